@@ -1,0 +1,91 @@
+"""ctypes binding of libalm_b200.so (the C ABI declared in include/alm_b200.h).
+
+There is no fallback: if the library is missing or a call fails, we raise.  The only torch
+objects that cross this boundary are raw `data_ptr()`s and the current CUDA stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libalm_b200.so"
+
+P = C.c_void_p
+I = C.c_int
+L = C.c_int64
+F = C.c_float
+
+# name -> argtypes (stream is always last and always a void*)
+SIGNATURES: dict[str, list] = {
+    "alm_gemm_bf16": [P, I, L, L, P, I, L, L, P, I, L, L, I, I, I, I, F, P, I, I, P],
+    "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, I, I, I, I, I, F, P],
+}
+
+
+class AlmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is explicit: `python -m audiolm_pytorch_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise AlmError(
+            f"{LIB_PATH} not found. Build it with `python -m audiolm_pytorch_b200.build` "
+            "(there is no CPU / PyTorch fallback for the hot path)."
+        )
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL | os.RTLD_NOW)
+    lib.alm_version.restype = I
+    lib.alm_status_string.restype = C.c_char_p
+    lib.alm_status_string.argtypes = [I]
+    lib.alm_launch_count.restype = C.c_ulonglong
+    lib.alm_reset_launch_count.restype = None
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = I
+    _lib = lib
+    return lib
+
+
+def ptr(t) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_handle() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    """Invoke `name(*args, current_stream)`; tensors are passed by address."""
+    lib = load()
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise AlmError(f"{name}: got a {a.device} tensor; the hot path has no CPU implementation")
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    rc = getattr(lib, name)(*conv, stream_handle())
+    if rc != 0:
+        raise AlmError(f"{name} failed: {lib.alm_status_string(rc).decode()} ({rc})")
+
+
+def launch_count() -> int:
+    return int(load().alm_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().alm_reset_launch_count()

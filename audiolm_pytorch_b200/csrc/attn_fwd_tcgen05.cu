@@ -1,0 +1,355 @@
+// Multi-query causal attention forward for sm_100a (replaces attend.py:69-146 as called from
+// audiolm_pytorch.py:390): softmax(q k^T * d^-1/2, masked by key-padding mask and right-aligned causal
+// mask) v, with ONE shared k/v head of width 64 for all query heads.
+//
+// One CTA = (batch b, head h, 128 queries).  Q K^T and P V run on tcgen05 with fp32 accumulators in
+// TMEM; Q/K/V tiles arrive by TMA into 128-B-swizzled smem; the softmax is an online (flash) softmax
+// held in registers by 128 threads (thread == query row == TMEM lane).
+//   warps 0-3 : softmax / rescale / output          warp 4 : TMA producer      warp 5 : UMMA issuer
+// TMEM: S[128x128] at columns 0..127, (P V)[128x64] at columns 128..191 (256 columns allocated so two
+// CTAs can be resident per SM and overlap each other's softmax and MMA phases).
+#include "alm_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace alm {
+
+constexpr int ATT_BM = 128;     // queries per CTA
+constexpr int ATT_BN = 128;     // keys per tile
+constexpr int ATT_D = 64;       // head width (dim_head)
+constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 SW128 tile
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 + 2 * ATT_KV_STAGES) + 256;  // 2 CTAs/SM: no align slack
+constexpr int ATT_TMEM_COLS = 256;
+
+struct AttnFwdParams {
+  __nv_bfloat16* o;       // [b, n_q, h*64] row stride ldo
+  float* lse;             // [b, h, n_q] natural-log LSE of the scaled scores (for backward); may be null
+  const uint8_t* kmask;   // [b, n_k] 1 = attend, 0 = masked; may be null
+  long long ldo;
+  int b, h, n_q, n_k;
+  int causal;
+  float scale_log2;       // d^-1/2 * log2(e)
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {  // SW128 tiles need 1024-B alignment
+    if (threadIdx.x == 0) printf("[alm] attn fwd: dynamic smem base not 1024-B aligned\n");
+    __trap();
+  }
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + ATT_TILE_BYTES;                   // two [128 x 64-key] tiles
+  uint8_t* sK = sP + 2 * ATT_TILE_BYTES;               // [stages]
+  uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;   // [stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                        // [stages]
+  uint64_t* kv_empty = kv_full + ATT_KV_STAGES;        // [stages]
+  uint64_t* s_full = kv_empty + ATT_KV_STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_qblocks = (p.n_q + ATT_BM - 1) / ATT_BM;
+  const int qb = n_qblocks - 1 - (int)blockIdx.x;  // heavy (late) query blocks first
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int q0 = qb * ATT_BM;
+  const int off = p.n_k - p.n_q;  // right alignment of queries against keys (KV cache)
+  int kv_end = p.n_k;
+  if (p.causal) kv_end = min(p.n_k, q0 + ATT_BM + off);
+  const int n_tiles = kv_end > 0 ? (kv_end + ATT_BN - 1) / ATT_BN : 0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);  // one arrive per softmax warp
+    mbar_init(pv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_PV = tmem_base + ATT_BN;
+
+  if (warp == 4) {
+    if (lane == 0 && n_tiles > 0) {
+      // ---------------- TMA producer ----------------
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, q0, batch);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_3d(sK + stage * ATT_TILE_BYTES, &tmK, &kv_full[stage], 0, j * ATT_BN, batch);
+        tma_load_3d(sV + stage * ATT_TILE_BYTES, &tmV, &kv_full[stage], 0, j * ATT_BN, batch);
+        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && n_tiles > 0) {
+      // ---------------- UMMA issuer ----------------
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(ATT_BM, ATT_BN, false, false);   // Q K^T
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(ATT_BM, ATT_D, false, true);    // P V (V is MN-major)
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int stage) {
+        const uint32_t k_addr = smem_u32(sK + stage * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 1024, 0),
+                       umma_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after_sync();
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(p_full, j & 1);
+        tc_fence_after_sync();
+        const uint32_t v_addr = smem_u32(sV + stage * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_bf16_ss(tmem_PV, umma_smem_desc_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
+                       umma_smem_desc_sw128(v_addr + k * 2048, 1024, 0), idesc_pv, k > 0 ? 1u : 0u);
+        umma_commit(pv_full);
+        umma_commit(&kv_empty[stage]);
+        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1u; }
+        if (j + 1 < n_tiles) {
+          mbar_wait(&kv_full[stage], phase);
+          tc_fence_after_sync();
+          issue_s(stage);  // S buffer is free: the softmax warps finished reading S_j before p_full
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread == query row ----------------
+    const int row = warp * 32 + lane;
+    const int qi = q0 + row;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    float o_acc[ATT_D];
+#pragma unroll
+    for (int d = 0; d < ATT_D; ++d) o_acc[d] = 0.f;
+    const int q_limit = p.causal ? qi + off : p.n_k - 1;  // last key index this query may see
+    const uint8_t* mrow = p.kmask ? p.kmask + (long long)batch * p.n_k : nullptr;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after_sync();
+      const int kbase = j * ATT_BN;
+      // key validity bits for this tile (uniform across the CTA except for the causal limit)
+      uint32_t valid[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (mrow != nullptr) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) {
+            const int kk = kbase + w * 32 + q4 * 16;
+            uint4 mv = make_uint4(0, 0, 0, 0);
+            if (kk + 16 <= p.n_k && ((reinterpret_cast<uintptr_t>(mrow + kk) & 15u) == 0)) {
+              mv = __ldg(reinterpret_cast<const uint4*>(mrow + kk));
+            } else {
+              uint8_t tmp[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) tmp[e] = (kk + e < p.n_k) ? __ldg(mrow + kk + e) : 0;
+              mv = *reinterpret_cast<uint4*>(tmp);
+            }
+            const uint32_t words[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if ((words[e >> 2] >> ((e & 3) * 8)) & 0xFFu) bits |= 1u << (q4 * 16 + e);
+          }
+          valid[w] = bits;
+        }
+      }
+      const int lim = min(q_limit, p.n_k - 1) - kbase;  // keys 0..lim of this tile are in range
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int hi = lim - w * 32;
+        const uint32_t range = hi >= 31 ? 0xFFFFFFFFu : (hi < 0 ? 0u : ((2u << hi) - 1u));
+        valid[w] &= range;
+      }
+
+      // pass 1: row max
+      float m_tile = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if ((valid[c] >> e) & 1u) m_tile = fmaxf(m_tile, __uint_as_float(r[e]));
+      }
+      const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_use);  // m_run == -inf -> 0
+      float l_tile = 0.f;
+
+      // previous tile's P V must have been consumed before sP is overwritten
+      if (j > 0) {
+        mbar_wait(pv_full, (j - 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(tmem_PV + lane_sel + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = o_acc[c * 32 + e] * alpha_prev + __uint_as_float(r[e]);
+        }
+      }
+
+      // pass 2: p = exp2(s*scale - m), write bf16 P into the SW128 K-major A-operand layout
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, r);
+        tmem_ld_wait();
+        float pe[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float s = __uint_as_float(r[e]);
+          const float pv = ((valid[c] >> e) & 1u) ? exp2f(s * p.scale_log2 - m_use) : 0.f;
+          pe[e] = pv;
+          l_tile += pv;
+        }
+        uint8_t* ptile = sP + (c >> 1) * ATT_TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(pe[g * 8 + 0], pe[g * 8 + 1]);
+          pk.y = pack_bf16x2(pe[g * 8 + 2], pe[g * 8 + 3]);
+          pk.z = pack_bf16x2(pe[g * 8 + 4], pe[g * 8 + 5]);
+          pk.w = pack_bf16x2(pe[g * 8 + 6], pe[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(ptile + sw128_offset(row, (c & 1) * 4 + g)) = pk;
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      alpha_prev = alpha;
+      // P (generic-proxy stores) -> visible to the tensor core (async proxy); S reads are complete
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // note: o_acc still lacks alpha for THIS tile; it is applied when P V of this tile is added
+      // (alpha_prev), i.e. o = o*alpha_j + PV_j.
+    }
+
+    if (n_tiles > 0) {
+      mbar_wait(pv_full, (n_tiles - 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(tmem_PV + lane_sel + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = o_acc[c * 32 + e] * alpha_prev + __uint_as_float(r[e]);
+      }
+    }
+    if (qi < p.n_q) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* dst = p.o + ((long long)batch * p.n_q + qi) * p.ldo + head * ATT_D;
+#pragma unroll
+      for (int g = 0; g < ATT_D / 8; ++g) {
+        uint4 pk;
+        pk.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
+        pk.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
+        pk.z = pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
+        pk.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+      }
+      if (p.lse != nullptr) {
+        const float lse = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : INFINITY;
+        p.lse[((long long)batch * p.h + head) * p.n_q + qi] = lse;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 5) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+}
+
+}  // namespace alm
+
+extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride,
+                                const void* v, int64_t ldv, int64_t v_bstride, const void* key_mask, void* o,
+                                int64_t ldo, float* lse, int b, int h, int n_q, int n_k, int causal, float scale,
+                                alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(q && k && v && o, ALM_ERR_ARG);
+  ALM_REQUIRE(b > 0 && h > 0 && n_q > 0 && n_k > 0 && n_k >= n_q, ALM_ERR_ARG);
+  ALM_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, ALM_ERR_ALIGN);
+  ALM_REQUIRE(k_bstride % 8 == 0 && v_bstride % 8 == 0, ALM_ERR_ALIGN);
+  ALM_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15u) == 0, ALM_ERR_ALIGN);
+
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {(uint64_t)h * ATT_D, (uint64_t)n_q, (uint64_t)b};
+    uint64_t strides[3] = {2, (uint64_t)ldq * 2, (uint64_t)n_q * ldq * 2};
+    uint32_t box[3] = {ATT_D, ATT_BM, 1};
+    int rc = make_tensor_map(&tmQ, q, 2, 3, dims, strides, box, true);
+    if (rc != ALM_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)ATT_D, (uint64_t)n_k, (uint64_t)b};
+    uint64_t strides[3] = {2, (uint64_t)ldk * 2, (uint64_t)k_bstride * 2};
+    uint32_t box[3] = {ATT_D, ATT_BN, 1};
+    int rc = make_tensor_map(&tmK, k, 2, 3, dims, strides, box, true);
+    if (rc != ALM_OK) return rc;
+    strides[1] = (uint64_t)ldv * 2;
+    strides[2] = (uint64_t)v_bstride * 2;
+    rc = make_tensor_map(&tmV, v, 2, 3, dims, strides, box, true);
+    if (rc != ALM_OK) return rc;
+  }
+  AttnFwdParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.lse = lse;
+  p.kmask = reinterpret_cast<const uint8_t*>(key_mask);
+  p.ldo = ldo;
+  p.b = b; p.h = h; p.n_q = n_q; p.n_k = n_k;
+  p.causal = causal;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ATT_SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((n_q + ATT_BM - 1) / ATT_BM, h, b);
+  mqa_attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
