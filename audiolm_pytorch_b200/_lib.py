@@ -22,7 +22,19 @@ F = C.c_float
 # name -> argtypes (stream is always last and always a void*)
 SIGNATURES: dict[str, list] = {
     "alm_gemm_bf16": [P, I, L, L, P, I, L, L, P, I, L, L, I, I, I, I, F, P, I, I, P],
-    "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, I, I, I, I, I, F, P],
+    "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, L, I, I, I, I, I, F, P],
+    "alm_mqa_attn_bwd": [P, L, P, L, L, P, L, L, P, L, P, P, P, I, P, L, P, L, P, L, I, I, I, I, I, F, P],
+    "alm_attn_delta": [P, L, P, L, P, L, I, I, I, P],
+    "alm_hc_pre_fwd": [P] * 12 + [P, P, P, P, P, I, I, I, P],
+    "alm_hc_pre_bwd": [P] * 12 + [P, P, P, P, P, P, P, P, P, F] + [P] * 8 + [I, I, I, P],
+    "alm_hc_post_fwd": [P, P, P, P, P, P, I, I, I, P],
+    "alm_hc_post_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+    "alm_geglu_ln_fwd": [P, L, I, P, P, L, P, I, I, I, P],
+    "alm_geglu_ln_bwd": [P, L, I, P, P, P, L, P, P, I, I, I, P],
+    "alm_ce_fwd_bwd": [P, L, P, L, P, P, L, P, P, I, I, I, P],
+    "alm_axpby_bf16": [P, L, F, P, L, F, P, L, L, I, P],
+    "alm_cast_pad_bf16": [P, L, P, L, L, I, I, P],
+    "alm_scale_by_scalar_bf16": [P, P, L, P],
 }
 
 

@@ -24,9 +24,9 @@ constexpr int ATT_TMEM_COLS = 256;
 
 struct AttnFwdParams {
   __nv_bfloat16* o;       // [b, n_q, h*64] row stride ldo
-  float* lse;             // [b, h, n_q] natural-log LSE of the scaled scores (for backward); may be null
+  float* lse;             // [b, h, lse_stride] natural-log LSE of the scaled scores (for backward); may be null
   const uint8_t* kmask;   // [b, n_k] 1 = attend, 0 = masked; may be null
-  long long ldo;
+  long long ldo, lse_stride;
   int b, h, n_q, n_k;
   int causal;
   float scale_log2;       // d^-1/2 * log2(e)
@@ -289,7 +289,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       if (p.lse != nullptr) {
         const float lse = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : INFINITY;
-        p.lse[((long long)batch * p.h + head) * p.n_q + qi] = lse;
+        p.lse[((long long)batch * p.h + head) * p.lse_stride + qi] = lse;
       }
     }
   }
@@ -304,7 +304,8 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride,
                                 const void* v, int64_t ldv, int64_t v_bstride, const void* key_mask, void* o,
-                                int64_t ldo, float* lse, int b, int h, int n_q, int n_k, int causal, float scale,
+                                int64_t ldo, float* lse, int64_t lse_stride, int b, int h, int n_q, int n_k, int causal,
+                                float scale,
                                 alm_stream_t stream_) {
   using namespace alm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -338,6 +339,7 @@ extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64
   p.lse = lse;
   p.kmask = reinterpret_cast<const uint8_t*>(key_mask);
   p.ldo = ldo;
+  p.lse_stride = lse_stride;
   p.b = b; p.h = h; p.n_q = n_q; p.n_k = n_k;
   p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;

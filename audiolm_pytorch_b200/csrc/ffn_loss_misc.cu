@@ -1,0 +1,379 @@
+// HBM-bound companions of the tensor-core GEMMs on the transformer path:
+//   geglu_ln   : GEGLU + inner LayerNorm of FeedForward (audiolm_pytorch.py:246-260), fwd + bwd
+//   ce         : cross entropy with ignore_index, fused forward + d(logits) (audiolm_pytorch.py:1561-1565,
+//                1836-1854, 2119-2137)
+//   attn_delta : rowsum(dO * O) for the attention backward
+//   axpby      : value-residual mix v = 0.5 (v + v_first) (audiolm_pytorch.py:355-358) and its backward
+//   cast_pad   : fp32 master weights -> zero-padded bf16 operand copies for the TMA/UMMA GEMMs
+#include "alm_common.cuh"
+
+namespace alm {
+
+constexpr int FF_THREADS = 256;
+constexpr int FF_MAX_CHUNKS = 4;  // inner_pad <= 256*8*4 = 8192
+
+__device__ __forceinline__ void unpack8b(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint32_t pk2b(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
+  return make_uint4(pk2b(f[0], f[1]), pk2b(f[2], f[3]), pk2b(f[4], f[5]), pk2b(f[6], f[7]));
+}
+
+template <int N>
+__device__ __forceinline__ void block_sum256(float (&v)[N], float* buf /*[N][8]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();  // protect buf from the previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) buf[i * 8 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < FF_THREADS / 32; ++w) s += buf[i * 8 + w];
+    v[i] = s;
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// h [M, ldh]: a = h[:, 0:inner], gate = h[:, gate_off : gate_off+inner]   ->  gn [M, ldg] (cols >= inner are 0)
+template <int NCH>
+__global__ void __launch_bounds__(FF_THREADS)
+geglu_ln_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate_off,
+                    const float* __restrict__ gamma, __nv_bfloat16* __restrict__ gn, long long ldg,
+                    float* __restrict__ stats, int M, int inner, int inner_pad) {
+  __shared__ float buf[2 * 8];
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    float g[NCH][8];
+    float s1[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[k][e] = 0.f;
+      if (c0 < inner_pad) {
+        float a[8], gt[8];
+        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a);
+        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          g[k][e] = (c0 + e < inner) ? gelu_erf(gt[e]) * a[e] : 0.f;
+          s1[0] += g[k][e];
+        }
+      }
+    }
+    block_sum256<1>(s1, buf);
+    const float mean = s1[0] / inner;
+    float s2[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < inner) s2[0] += (g[k][e] - mean) * (g[k][e] - mean);
+    }
+    block_sum256<1>(s2, buf);
+    const float rstd = rsqrtf(s2[0] / inner + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+      if (c0 < inner_pad) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (c0 + e < inner) ? (g[k][e] - mean) * rstd * gamma[c0 + e] : 0.f;
+        *reinterpret_cast<uint4*>(gn + (size_t)m * ldg + c0) = pack8b(o);
+      }
+    }
+    if (threadIdx.x == 0) {
+      stats[(size_t)m * 2] = mean;
+      stats[(size_t)m * 2 + 1] = rstd;
+    }
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(FF_THREADS)
+geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate_off,
+                    const float* __restrict__ gamma, const float* __restrict__ stats,
+                    const __nv_bfloat16* __restrict__ dgn, long long ldg, __nv_bfloat16* __restrict__ dh,
+                    float* __restrict__ g_gamma, int M, int inner, int inner_pad) {
+  __shared__ float buf[2 * 8];
+  float gacc[NCH][8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gacc[k][e] = 0.f;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const float mean = stats[(size_t)m * 2], rstd = stats[(size_t)m * 2 + 1];
+    float a[NCH][8], gt[NCH][8], gl[NCH][8], xh[NCH][8];
+    float r2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[k][e] = gt[k][e] = gl[k][e] = xh[k][e] = 0.f; }
+      if (c0 < inner_pad) {
+        float dv[8];
+        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a[k]);
+        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt[k]);
+        unpack8b(*reinterpret_cast<const uint4*>(dgn + (size_t)m * ldg + c0), dv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (c0 + e < inner) {
+            const float g = gelu_erf(gt[k][e]) * a[k][e];
+            xh[k][e] = (g - mean) * rstd;
+            gl[k][e] = dv[e] * gamma[c0 + e];
+            gacc[k][e] += dv[e] * xh[k][e];
+            r2[0] += gl[k][e];
+            r2[1] += gl[k][e] * xh[k][e];
+          }
+        }
+      }
+    }
+    block_sum256<2>(r2, buf);
+    const float m1 = r2[0] / inner, m2 = r2[1] / inner;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+      if (c0 < inner_pad) {
+        float da[8], dg8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (c0 + e < inner) {
+            const float dg = rstd * (gl[k][e] - m1 - xh[k][e] * m2);
+            da[e] = dg * gelu_erf(gt[k][e]);
+            dg8[e] = dg * a[k][e] * gelu_erf_grad(gt[k][e]);
+          } else {
+            da[e] = dg8[e] = 0.f;
+          }
+        }
+        *reinterpret_cast<uint4*>(dh + (size_t)m * ldh + c0) = pack8b(da);
+        *reinterpret_cast<uint4*>(dh + (size_t)m * ldh + gate_off + c0) = pack8b(dg8);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (c0 + e < inner) atomicAdd(g_gamma + c0 + e, gacc[k][e]);
+  }
+}
+
+// ---- cross entropy: one CTA per row -----------------------------------------------------------
+// loss_rows[r] = lse - logit[label]  (0 when label == ignore)
+// dlogits[r, c] = (softmax - onehot) * (*scale_num) / (*scale_den)   as bf16 (0 row when ignored)
+__global__ void __launch_bounds__(FF_THREADS)
+ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ldl, const long long* __restrict__ labels,
+                  long long ignore_index, float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits,
+                  long long ldd, const float* __restrict__ scale_num, const float* __restrict__ scale_den, int V,
+                  int Vpad) {
+  __shared__ float buf[2 * 8];
+  const int r = blockIdx.x;
+  const float* row = logits + (size_t)r * ldl;
+  const long long label = labels[r];
+  const bool ignored = (label == ignore_index);
+  float mx[1] = {-INFINITY};
+  for (int c = threadIdx.x; c < V; c += FF_THREADS) mx[0] = fmaxf(mx[0], row[c]);
+  // block max via the sum helper's buffer
+  {
+    float v = warp_max(mx[0]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float m = buf[0];
+#pragma unroll
+    for (int w = 1; w < FF_THREADS / 32; ++w) m = fmaxf(m, buf[w]);
+    mx[0] = m;
+  }
+  float sm[1] = {0.f};
+  for (int c = threadIdx.x; c < V; c += FF_THREADS) sm[0] += __expf(row[c] - mx[0]);
+  block_sum256<1>(sm, buf);
+  const float lse = mx[0] + logf(sm[0]);
+  if (threadIdx.x == 0) loss_rows[r] = ignored ? 0.f : (lse - row[label]);
+  if (dlogits != nullptr) {
+    const float sc = ignored ? 0.f : (*scale_num) / (*scale_den);
+    __nv_bfloat16* drow = dlogits + (size_t)r * ldd;
+    for (int c = threadIdx.x; c < Vpad; c += FF_THREADS) {
+      float g = 0.f;
+      if (c < V && !ignored) g = (__expf(row[c] - lse) - (c == label ? 1.f : 0.f)) * sc;
+      drow[c] = __float2bfloat16_rn(g);
+    }
+  }
+}
+
+// ---- delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per (token, head), d = 64) --------
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo,
+                                  const __nv_bfloat16* __restrict__ d_o, long long lddo, float* __restrict__ delta,
+                                  long long dstride, int b, int h, int n) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = b * n * h;
+  if (gw >= total) return;
+  const int head = gw % h;
+  const int tok = gw / h;  // b*n + i
+  const uint32_t uo = *reinterpret_cast<const uint32_t*>(o + (size_t)tok * ldo + head * 64 + lane * 2);
+  const uint32_t ud = *reinterpret_cast<const uint32_t*>(d_o + (size_t)tok * lddo + head * 64 + lane * 2);
+  float v = bf16_lo(uo) * bf16_lo(ud) + bf16_hi(uo) * bf16_hi(ud);
+  v = warp_sum(v);
+  if (lane == 0) {
+    const int bi = tok / n, i = tok - bi * n;
+    delta[((size_t)bi * h + head) * dstride + i] = v;
+  }
+}
+
+// ---- out[r, c] = alpha * x[r, c] + beta * y[r, c]   (bf16, 2-D strided, cols % 2 == 0) ---------
+__global__ void axpby_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float alpha,
+                                  const __nv_bfloat16* __restrict__ y, long long ldy, float beta,
+                                  __nv_bfloat16* __restrict__ out, long long ldout, long long rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = cols / 2;
+  if (i >= rows * half) return;
+  const long long r = i / half;
+  const int c = (int)(i - r * half) * 2;
+  const uint32_t ux = *reinterpret_cast<const uint32_t*>(x + r * ldx + c);
+  float lo = alpha * bf16_lo(ux), hi = alpha * bf16_hi(ux);
+  if (y != nullptr) {
+    const uint32_t uy = *reinterpret_cast<const uint32_t*>(y + r * ldy + c);
+    lo += beta * bf16_lo(uy);
+    hi += beta * bf16_hi(uy);
+  }
+  *reinterpret_cast<uint32_t*>(out + r * ldout + c) = pk2b(lo, hi);
+}
+
+// ---- dst_bf16[r, 0:cols_pad] = src_f32[r, 0:cols] zero padded -----------------------------------
+__global__ void cast_pad_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                long long ldd, long long rows, int cols, int cols_pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols_pad) return;
+  const long long r = i / cols_pad;
+  const int c = (int)(i - r * cols_pad);
+  dst[r * ldd + c] = __float2bfloat16_rn(c < cols ? src[r * lds + c] : 0.f);
+}
+
+// ---- x[i] *= *s (bf16, contiguous) ---------------------------------------------------------------
+__global__ void scale_by_scalar_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ s, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * (*s));
+}
+
+}  // namespace alm
+
+using namespace alm;
+
+extern "C" int alm_geglu_ln_fwd(const void* h, int64_t ldh, int gate_off, const float* gamma, void* gn, int64_t ldg,
+                                float* stats, int M, int inner, int inner_pad, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(M > 0 && inner > 0 && inner_pad >= inner && inner_pad % 8 == 0, ALM_ERR_ARG);
+  ALM_REQUIRE(ldh % 8 == 0 && ldg % 8 == 0 && gate_off % 8 == 0, ALM_ERR_ALIGN);
+  const int nch = ceil_div(inner_pad / 8, FF_THREADS);
+  ALM_REQUIRE(nch <= FF_MAX_CHUNKS, ALM_ERR_UNSUPPORTED);
+  const int grid = min(M, num_sms() * 8);
+  auto* hp = (const __nv_bfloat16*)h;
+  auto* gp = (__nv_bfloat16*)gn;
+  if (nch <= 1) geglu_ln_fwd_kernel<1><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
+  else if (nch == 2) geglu_ln_fwd_kernel<2><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
+  else geglu_ln_fwd_kernel<4><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_geglu_ln_bwd(const void* h, int64_t ldh, int gate_off, const float* gamma, const float* stats,
+                                const void* dgn, int64_t ldg, void* dh, float* g_gamma, int M, int inner,
+                                int inner_pad, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(M > 0 && inner > 0 && inner_pad >= inner && inner_pad % 8 == 0, ALM_ERR_ARG);
+  ALM_REQUIRE(ldh % 8 == 0 && ldg % 8 == 0 && gate_off % 8 == 0, ALM_ERR_ALIGN);
+  const int nch = ceil_div(inner_pad / 8, FF_THREADS);
+  ALM_REQUIRE(nch <= FF_MAX_CHUNKS, ALM_ERR_UNSUPPORTED);
+  const int grid = min(M, num_sms() * 4);
+  auto* hp = (const __nv_bfloat16*)h;
+  auto* dg = (const __nv_bfloat16*)dgn;
+  auto* dhp = (__nv_bfloat16*)dh;
+  if (nch <= 1) geglu_ln_bwd_kernel<1><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+  else if (nch == 2) geglu_ln_bwd_kernel<2><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+  else geglu_ln_bwd_kernel<4><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_ce_fwd_bwd(const float* logits, int64_t ldl, const int64_t* labels, int64_t ignore_index,
+                              float* loss_rows, void* dlogits, int64_t ldd, const float* scale_num,
+                              const float* scale_den, int rows, int V, int Vpad, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(rows > 0 && V > 0 && Vpad >= V, ALM_ERR_ARG);
+  ALM_REQUIRE(dlogits == nullptr || (scale_num && scale_den), ALM_ERR_ARG);
+  ce_fwd_bwd_kernel<<<rows, FF_THREADS, 0, stream>>>(logits, ldl, (const long long*)labels, ignore_index,
+                                                    loss_rows, (__nv_bfloat16*)dlogits, ldd, scale_num, scale_den, V,
+                                                    Vpad);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_attn_delta(const void* o, int64_t ldo, const void* d_o, int64_t lddo, float* delta,
+                              int64_t delta_stride, int b, int h, int n, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(b > 0 && h > 0 && n > 0, ALM_ERR_ARG);
+  const long long warps = (long long)b * h * n;
+  const int threads = 256;
+  const long long blocks = ceil_div(warps * 32, (long long)threads);
+  attn_delta_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)o, ldo,
+                                                              (const __nv_bfloat16*)d_o, lddo, delta, delta_stride, b, h, n);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_axpby_bf16(const void* x, int64_t ldx, float alpha, const void* y, int64_t ldy, float beta,
+                              void* out, int64_t ldout, int64_t rows, int cols, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(rows > 0 && cols > 0 && cols % 2 == 0, ALM_ERR_ARG);
+  ALM_REQUIRE(ldx % 2 == 0 && ldy % 2 == 0 && ldout % 2 == 0, ALM_ERR_ALIGN);
+  const long long n = rows * (cols / 2);
+  axpby_bf16_kernel<<<(unsigned)ceil_div(n, 256LL), 256, 0, stream>>>(
+      (const __nv_bfloat16*)x, ldx, alpha, (const __nv_bfloat16*)y, ldy, beta, (__nv_bfloat16*)out, ldout, rows, cols);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_cast_pad_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols,
+                                 int cols_pad, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(rows > 0 && cols > 0 && cols_pad >= cols, ALM_ERR_ARG);
+  const long long n = rows * cols_pad;
+  cast_pad_kernel<<<(unsigned)ceil_div(n, 256LL), 256, 0, stream>>>(src, lds, (__nv_bfloat16*)dst, ldd, rows, cols,
+                                                                   cols_pad);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_scale_by_scalar_bf16(void* x, const float* s, int64_t n, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(n > 0 && s, ALM_ERR_ARG);
+  scale_by_scalar_kernel<<<(unsigned)ceil_div((long long)n, 256LL), 256, 0, stream>>>((__nv_bfloat16*)x, s, n);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}

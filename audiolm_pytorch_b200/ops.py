@@ -80,7 +80,8 @@ def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, retu
     assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
     assert q.stride(0) == n_q * q.stride(1)
     o = torch.empty(b, n_q, hd, device=q.device, dtype=bf16)
-    lse = torch.empty(b, heads, n_q, device=q.device, dtype=f32) if return_lse else None
+    n_q_pad = (n_q + 127) // 128 * 128  # the backward stages lse rows with 512-B bulk copies
+    lse = torch.empty(b, heads, n_q_pad, device=q.device, dtype=f32) if return_lse else None
     if key_mask is not None:
         key_mask = key_mask.to(torch.uint8).contiguous()
         assert key_mask.shape == (b, n_k)
@@ -89,6 +90,150 @@ def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, retu
     _lib.call(
         "alm_mqa_attn_fwd",
         q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), key_mask,
-        o, o.stride(1), lse, b, heads, n_q, n_k, int(causal), float(scale),
+        o, o.stride(1), lse, n_q_pad, b, heads, n_q, n_k, int(causal), float(scale),
     )
     return o, lse
+
+
+def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, scale=None):
+    """Backward of mqa_attn_fwd: returns dq [b,n_q,h*64], dk [b,n_k,64], dv [b,n_k,64] (bf16).
+
+    lse is the padded [b, heads, n_q_pad] tensor returned by the forward.
+    """
+    _check_cuda(q, k, v, o, d_o, lse, key_mask)
+    b, n_q, hd = q.shape
+    n_k = k.shape[1]
+    n_q_pad = lse.shape[-1]
+    assert d_o.dtype == bf16 and d_o.stride(-1) == 1 and o.stride(-1) == 1
+    assert d_o.stride(0) == n_q * d_o.stride(1)
+    delta = torch.empty(b, heads, n_q_pad, device=q.device, dtype=f32)
+    _lib.call("alm_attn_delta", o, o.stride(1), d_o, d_o.stride(1), delta, n_q_pad, b, heads, n_q)
+    if key_mask is not None:
+        key_mask = key_mask.to(torch.uint8).contiguous()
+    if scale is None:
+        scale = 64 ** -0.5
+    dq = torch.empty(b, n_q, hd, device=q.device, dtype=bf16)
+    dk = torch.empty(b, n_k, 64, device=q.device, dtype=bf16)
+    dv = torch.empty(b, n_k, 64, device=q.device, dtype=bf16)
+    _lib.call(
+        "alm_mqa_attn_bwd",
+        q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), d_o, d_o.stride(1), key_mask,
+        lse, delta, n_q_pad, dq, dq.stride(1), dk, dk.stride(1), dv, dv.stride(1),
+        b, heads, n_q, n_k, int(causal), float(scale),
+    )
+    return dq, dk, dv
+
+
+HC_AUX = 30  # floats of per-token state kept for the backward (see csrc/hyper_conn.cu)
+
+
+def _hc_param_ptrs(hc, ln_gamma):
+    return (hc["gamma"], hc["dyn_alpha"], hc["dyn_beta"], hc["static_alpha"], hc["static_beta"],
+            hc["alpha_scale"], hc["beta_scale"], ln_gamma)
+
+
+def hc_pre_fwd(hc, ln_gamma, *, R_in=None, Y=None, beta_prev=None, x_expand=None, M, d, streams=4):
+    """depth(prev branch) + width(this branch) + pre-LayerNorm.  hc: dict of fp32 HC params.
+
+    Returns R_out [M,S,d] bf16, bin [M,d] bf16, xn [M,d] bf16, beta [M,S] f32, aux [M,30] f32.
+    """
+    dev = ln_gamma.device
+    R_out = torch.empty(M, streams, d, device=dev, dtype=bf16)
+    bin_ = torch.empty(M, d, device=dev, dtype=bf16)
+    xn = torch.empty(M, d, device=dev, dtype=bf16)
+    beta = torch.empty(M, streams, device=dev, dtype=f32)
+    aux = torch.empty(M, HC_AUX, device=dev, dtype=f32)
+    _lib.call("alm_hc_pre_fwd", R_in, Y, beta_prev, x_expand, *_hc_param_ptrs(hc, ln_gamma),
+              R_out, bin_, xn, beta, aux, M, d, streams)
+    return R_out, bin_, xn, beta, aux
+
+
+def hc_pre_bwd(hc, ln_gamma, grads, g_ln_gamma, aux, dR_out, dxn, dbeta, *, dbin_extra=None, R_in=None, Y=None,
+               beta_prev=None, x_expand=None, dx_scale=1.0, M, d, streams=4):
+    """Backward of hc_pre_fwd.  `grads`: dict of fp32 accumulators shaped like `hc` (atomically added to).
+
+    Returns (dR_in, dY, dbeta_prev) or dx_expand [M,d] f32 when the op expanded the streams.
+    """
+    dev = ln_gamma.device
+    if x_expand is not None:
+        dx = torch.empty(M, d, device=dev, dtype=f32)
+        dR_in = dY = dbp = None
+    else:
+        dx = None
+        dR_in = torch.empty(M, streams, d, device=dev, dtype=bf16)
+        dY = torch.empty(M, d, device=dev, dtype=bf16)
+        dbp = torch.empty(M, streams, device=dev, dtype=f32)
+    _lib.call("alm_hc_pre_bwd", R_in, Y, beta_prev, x_expand, *_hc_param_ptrs(hc, ln_gamma), aux, dR_out, dxn,
+              dbin_extra, dbeta, dR_in, dY, dbp, dx, float(dx_scale),
+              grads["gamma"], grads["dyn_alpha"], grads["dyn_beta"], grads["static_alpha"], grads["static_beta"],
+              grads["alpha_scale"], grads["beta_scale"], g_ln_gamma, M, d, streams)
+    return dx if x_expand is not None else (dR_in, dY, dbp)
+
+
+def hc_post_fwd(R_in, Y, beta_prev, ln_gamma, *, M, d, streams=4):
+    out = torch.empty(M, d, device=R_in.device, dtype=bf16)
+    stats = torch.empty(M, 2, device=R_in.device, dtype=f32)
+    _lib.call("alm_hc_post_fwd", R_in, Y, beta_prev, ln_gamma, out, stats, M, d, streams)
+    return out, stats
+
+
+def hc_post_bwd(R_in, Y, beta_prev, ln_gamma, stats, dout, g_ln_gamma, *, M, d, streams=4):
+    dR_in = torch.empty(M, streams, d, device=R_in.device, dtype=bf16)
+    dY = torch.empty(M, d, device=R_in.device, dtype=bf16)
+    dbp = torch.empty(M, streams, device=R_in.device, dtype=f32)
+    _lib.call("alm_hc_post_bwd", R_in, Y, beta_prev, ln_gamma, stats, dout, dR_in, dY, dbp, g_ln_gamma, M, d, streams)
+    return dR_in, dY, dbp
+
+
+def geglu_ln_fwd(h, gamma, *, inner, inner_pad):
+    """h [M, 2*inner_pad] bf16 (a | gate) -> gn [M, inner_pad] bf16 = LN(gelu(gate)*a)*gamma, stats [M,2]."""
+    M = h.shape[0]
+    gn = torch.empty(M, inner_pad, device=h.device, dtype=bf16)
+    stats = torch.empty(M, 2, device=h.device, dtype=f32)
+    _lib.call("alm_geglu_ln_fwd", h, h.stride(0), inner_pad, gamma, gn, gn.stride(0), stats, M, inner, inner_pad)
+    return gn, stats
+
+
+def geglu_ln_bwd(h, gamma, stats, dgn, g_gamma, *, inner, inner_pad):
+    M = h.shape[0]
+    dh = torch.empty_like(h)
+    assert dh.stride(0) == h.stride(0)
+    _lib.call("alm_geglu_ln_bwd", h, h.stride(0), inner_pad, gamma, stats, dgn, dgn.stride(0), dh, g_gamma, M,
+              inner, inner_pad)
+    return dh
+
+
+def ce_fwd_bwd(logits, labels, *, ignore_index=-1, scale_num=None, scale_den=None, want_grad=True):
+    """logits [R, V] f32 (row stride free), labels [R] int64 -> loss_rows [R] f32, dlogits [R, Vpad] bf16."""
+    R, V = logits.shape
+    Vpad = (V + 7) // 8 * 8
+    loss_rows = torch.empty(R, device=logits.device, dtype=f32)
+    dlogits = torch.empty(R, Vpad, device=logits.device, dtype=bf16) if want_grad else None
+    _lib.call("alm_ce_fwd_bwd", logits, logits.stride(0), labels, int(ignore_index), loss_rows, dlogits,
+              Vpad, scale_num, scale_den, R, V, Vpad)
+    return loss_rows, dlogits
+
+
+def axpby(x, alpha, y, beta, out=None):
+    """out = alpha*x + beta*y on 2-D bf16 views (last dim contiguous)."""
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(rows, cols, device=x.device, dtype=bf16)
+    _lib.call("alm_axpby_bf16", x, x.stride(0), float(alpha), y, y.stride(0) if y is not None else 0, float(beta),
+              out, out.stride(0), rows, cols)
+    return out
+
+
+def cast_pad(src, cols_pad=None, out=None):
+    """fp32 [R, C] (last dim contiguous) -> bf16 [R, cols_pad] zero padded."""
+    rows, cols = src.shape
+    cols_pad = cols if cols_pad is None else cols_pad
+    if out is None:
+        out = torch.empty(rows, cols_pad, device=src.device, dtype=bf16)
+    _lib.call("alm_cast_pad_bf16", src, src.stride(0), out, out.stride(0), rows, cols, cols_pad)
+    return out
+
+
+def scale_by_scalar(x, s):
+    _lib.call("alm_scale_by_scalar_bf16", x, s, x.numel())
+    return x

@@ -60,15 +60,86 @@ int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const v
  * o[b,i,h*64:(h+1)*64] = softmax_j( q[b,i,h,:]·k[b,j,:] * scale, masked ) · v[b,j,:]
  *   one shared k/v head of width 64 (MQA); key_mask[b,j] (uint8, 1 = attend) optional;
  *   causal: query i sees keys j <= i + (n_k - n_q) (right-aligned, as needed by the KV cache).
- *   lse[b,h,i] (optional) = log-sum-exp of the scaled, masked scores (natural log) for the backward.
+ *   lse[b,h,i] (optional, row stride lse_stride >= n_q) = log-sum-exp of the scaled, masked scores (natural log) for the backward.
  * Replaces Attend.forward / flash_attn (attend.py:69-146) as called by Attention.forward
  * (audiolm_pytorch.py:390).  Fully masked rows produce zeros (the reference's flash path yields NaN).
  * q rows stride ldq (q may be a column slice of a fused qkv buffer); k/v rows stride ldk/ldv, batch
  * strides k_bstride/v_bstride (elements).
  */
 int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride, const void* v,
-                     int64_t ldv, int64_t v_bstride, const void* key_mask, void* o, int64_t ldo, float* lse, int b,
-                     int h, int n_q, int n_k, int causal, float scale, alm_stream_t stream);
+                     int64_t ldv, int64_t v_bstride, const void* key_mask, void* o, int64_t ldo, float* lse,
+                     int64_t lse_stride, int b, int h, int n_q, int n_k, int causal, float scale,
+                     alm_stream_t stream);
+
+/*
+ * Backward of alm_mqa_attn_fwd (two tcgen05 kernels: dK/dV per key block accumulating over all heads
+ * in TMEM, then dQ per query block).  lse/delta are [b, h, n_q_pad] with n_q_pad a multiple of 128;
+ * delta = rowsum(dO * O) from alm_attn_delta.  Autograd of attend.py:69-146.
+ */
+int alm_mqa_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride, const void* v,
+                     int64_t ldv, int64_t v_bstride, const void* d_o, int64_t lddo, const void* key_mask,
+                     const float* lse, const float* delta, int n_q_pad, void* dq, int64_t lddq, void* dk,
+                     int64_t lddk, void* dv, int64_t lddv, int b, int h, int n_q, int n_k, int causal, float scale,
+                     alm_stream_t stream);
+int alm_attn_delta(const void* o, int64_t ldo, const void* d_o, int64_t lddo, float* delta /* [b,h,stride] */,
+                   int64_t delta_stride, int b, int h, int n, alm_stream_t stream);
+
+/* ---- Hyper-Connections residual streams fused with the pre-LayerNorm (HBM-bound) ---------------- */
+/*
+ * Internal layout: residual streams R [M, S=4, d] bf16, M = batch*seq.  One call per branch does
+ *   R      = R_in + beta_prev (x) Y          depth connection of the previous branch
+ *            (or R_s = x_expand for all s: expand_streams, audiolm_pytorch.py:524)
+ *   bin, R_out = width connection of this branch (dynamic+static alpha/beta, RMSNorm over channels)
+ *   xn     = LayerNorm(bin) * ln_gamma       the branch's pre-norm (audiolm_pytorch.py:347, 254)
+ * aux [M, 30] keeps tanh pre-activations, 1/|R_s| and the LN mean/rstd for the backward.
+ * Replaces hyper_connections.HyperConnections.forward as used at audiolm_pytorch.py:446-454,
+ * 528-547 (third-party; restated in oracle/third_party.py).  Only streams == 4 is built.
+ */
+int alm_hc_pre_fwd(const void* R_in, const void* Y, const float* beta_prev, const float* x_expand,
+                   const float* gamma_hc, const float* dyn_alpha, const float* dyn_beta, const float* static_alpha,
+                   const float* static_beta, const float* alpha_scale, const float* beta_scale,
+                   const float* ln_gamma, void* R_out, void* bin, void* xn, float* beta_out, float* aux, int M,
+                   int d, int streams, alm_stream_t stream);
+int alm_hc_pre_bwd(const void* R_in, const void* Y, const float* beta_prev, const float* x_expand,
+                   const float* gamma_hc, const float* dyn_alpha, const float* dyn_beta, const float* static_alpha,
+                   const float* static_beta, const float* alpha_scale, const float* beta_scale,
+                   const float* ln_gamma, const float* aux, const void* dR_out, const void* dxn,
+                   const void* dbin_extra, const float* dbeta, void* dR_in, void* dY, float* dbeta_prev,
+                   float* dx_expand, float dx_scale, float* g_gamma_hc, float* g_dyn_alpha, float* g_dyn_beta,
+                   float* g_static_alpha, float* g_static_beta, float* g_alpha_scale, float* g_beta_scale,
+                   float* g_ln_gamma, int M, int d, int streams, alm_stream_t stream);
+/* last depth connection + reduce_streams (sum) + final LayerNorm (audiolm_pytorch.py:551-555) */
+int alm_hc_post_fwd(const void* R_in, const void* Y, const float* beta_prev, const float* ln_gamma, void* out,
+                    float* stats, int M, int d, int streams, alm_stream_t stream);
+int alm_hc_post_bwd(const void* R_in, const void* Y, const float* beta_prev, const float* ln_gamma,
+                    const float* stats, const void* dout, void* dR_in, void* dY, float* dbeta_prev,
+                    float* g_ln_gamma, int M, int d, int streams, alm_stream_t stream);
+
+/* ---- FeedForward inner part: GEGLU + LayerNorm(inner) (audiolm_pytorch.py:246-258) -------------- */
+/* h [M, ldh] bf16 holds a = h[:, 0:inner] and gate = h[:, gate_off:gate_off+inner];
+ * gn[M, ldg] = LN(gelu(gate) * a) * gamma, columns [inner, inner_pad) are written as zeros. */
+int alm_geglu_ln_fwd(const void* h, int64_t ldh, int gate_off, const float* gamma, void* gn, int64_t ldg,
+                     float* stats, int M, int inner, int inner_pad, alm_stream_t stream);
+int alm_geglu_ln_bwd(const void* h, int64_t ldh, int gate_off, const float* gamma, const float* stats,
+                     const void* dgn, int64_t ldg, void* dh, float* g_gamma, int M, int inner, int inner_pad,
+                     alm_stream_t stream);
+
+/* ---- cross entropy with ignore_index, fused forward + d(logits) --------------------------------- */
+/* loss_rows[r] = lse(logits[r]) - logits[r, label]  (0 if label == ignore_index);
+ * dlogits[r, 0:Vpad] (bf16, optional) = (softmax - onehot) * (*scale_num / *scale_den).
+ * Replaces F.cross_entropy at audiolm_pytorch.py:1561-1565, 1839-1849, 2122-2132. */
+int alm_ce_fwd_bwd(const float* logits, int64_t ldl, const int64_t* labels, int64_t ignore_index, float* loss_rows,
+                   void* dlogits, int64_t ldd, const float* scale_num, const float* scale_den, int rows, int V,
+                   int Vpad, alm_stream_t stream);
+
+/* ---- small helpers on the same path ------------------------------------------------------------- */
+/* out = alpha*x + beta*y (bf16, 2-D strided): value-residual mix v = 0.5 (v + v_first), :355-358 */
+int alm_axpby_bf16(const void* x, int64_t ldx, float alpha, const void* y, int64_t ldy, float beta, void* out,
+                   int64_t ldout, int64_t rows, int cols, alm_stream_t stream);
+/* fp32 master weights -> zero-padded bf16 GEMM operands (what autocast does at every Linear) */
+int alm_cast_pad_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, int cols_pad,
+                      alm_stream_t stream);
+int alm_scale_by_scalar_bf16(void* x, const float* s, int64_t n, alm_stream_t stream);
 
 #ifdef __cplusplus
 }
