@@ -1,0 +1,474 @@
+"""Transformer blocks of the AudioLM hot path, running on libalm_b200 (sm_100a).
+
+Class names, constructor kwargs and state_dict keys follow the reference
+(/root/reference/audiolm_pytorch/audiolm_pytorch.py:191-560, attend.py:35-146) so checkpoints load
+unchanged; the arithmetic is one hand-orchestrated forward/backward over the C-ABI kernels:
+
+    per branch:   [hc_pre: depth(prev) + width + LayerNorm]  ->  tcgen05 GEMMs / attention / GEGLU+LN
+    end of stack: [hc_post: depth + reduce_streams + final LayerNorm]
+
+Activations are bf16 with fp32 accumulation (the reference's bf16-autocast numerics), parameters stay
+fp32 `nn.Parameter`s; padded bf16 operand copies are rebuilt only when a parameter's version changes.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def exists(v):
+    return v is not None
+
+
+def default(v, d):
+    return v if exists(v) else d
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter containers (same attribute names -> same state_dict keys as the reference)
+# ----------------------------------------------------------------------------------------------
+class LayerNorm(nn.Module):
+    """gamma parameter + zero `beta` buffer (audiolm_pytorch.py:191-198)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+        self.register_buffer("beta", torch.zeros(dim))
+
+
+class Attend(nn.Module):
+    """attend.py:35-146.  Holds the configuration; the math runs in alm_mqa_attn_fwd/bwd."""
+
+    def __init__(self, dropout=0.0, causal=False, flash=False):
+        super().__init__()
+        self.dropout = dropout
+        self.causal = causal
+        self.flash = flash
+
+    def forward(self, q, k, v, mask=None, attn_bias=None):
+        """q [b h n 64], k/v [b j 64] -> [b h n 64] (inference helper; training goes through Transformer)."""
+        if exists(attn_bias):
+            raise NotImplementedError("additive attention bias (rel_pos_bias path) is not built yet")
+        b, h, n, d = q.shape
+        qf = q.permute(0, 2, 1, 3).reshape(b, n, h * d).to(bf16).contiguous()
+        o, _ = ops.mqa_attn_fwd(qf, k.to(bf16).contiguous(), v.to(bf16).contiguous(), heads=h, key_mask=mask,
+                                causal=self.causal, return_lse=False)
+        return o.reshape(b, n, h, d).permute(0, 2, 1, 3)
+
+
+class Attention(nn.Module):
+    """Parameter holder for audiolm_pytorch.py:264-406 (self-attention, multi-query, dim_head 64)."""
+
+    def __init__(self, dim, causal=False, dim_head=64, dim_context=None, heads=8, norm_context=False,
+                 num_null_kv=0, dropout=0.1, scale=8, flash=False):
+        super().__init__()
+        if dim_head != 64:
+            raise NotImplementedError("the sm_100a attention kernels are built for dim_head=64")
+        if num_null_kv > 0 or exists(dim_context) and dim_context != dim:
+            raise NotImplementedError("cross attention / null kv (text conditioning) is out of scope")
+        self.heads = heads
+        self.causal = causal
+        inner = dim_head * heads
+        self.norm = LayerNorm(dim)
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, dim_head * 2, bias=False)
+        self.attend = Attend(flash=flash, dropout=dropout, causal=causal)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), nn.Dropout(dropout))
+
+
+class FeedForward(nn.Module):
+    """audiolm_pytorch.py:251-260 with the reference's Sequential indices as attribute names
+    (0: LayerNorm, 1: Linear(d, 2*inner), 3: LayerNorm(inner), 5: Linear(inner, d))."""
+
+    def __init__(self, dim, mult=4, dropout=0.1):
+        super().__init__()
+        inner = int(dim * 2 * mult / 3)
+        self.inner = inner
+        self.add_module("0", LayerNorm(dim))
+        self.add_module("1", nn.Linear(dim, inner * 2, bias=False))
+        self.add_module("3", LayerNorm(inner))
+        self.add_module("5", nn.Linear(inner, dim, bias=False))
+
+
+class _StreamNorm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.zeros(dim))
+
+
+class HyperConnections(nn.Module):
+    """Parameters of hyper_connections.HyperConnections (third party; audiolm_pytorch.py:446-454)."""
+
+    def __init__(self, num_residual_streams, *, dim, branch, layer_index=None):
+        super().__init__()
+        s = num_residual_streams
+        self.num_residual_streams = s
+        self.branch = branch
+        self.norm = _StreamNorm(dim)
+        init = (layer_index if exists(layer_index) else int(torch.randint(0, s, ()).item())) % s
+        self.static_beta = nn.Parameter(torch.ones(s))
+        a0 = torch.zeros(s, 1)
+        a0[init, 0] = 1.0
+        self.static_alpha = nn.Parameter(torch.cat((a0, torch.eye(s)), dim=1))
+        self.dynamic_alpha_fn = nn.Parameter(torch.zeros(dim, s + 1))
+        self.dynamic_alpha_scale = nn.Parameter(torch.ones(()) * 1e-2)
+        self.dynamic_beta_fn = nn.Parameter(torch.zeros(dim))
+        self.dynamic_beta_scale = nn.Parameter(torch.ones(()) * 1e-2)
+
+    def kernel_params(self):
+        return dict(gamma=self.norm.gamma, dyn_alpha=self.dynamic_alpha_fn, dyn_beta=self.dynamic_beta_fn,
+                    static_alpha=self.static_alpha, static_beta=self.static_beta,
+                    alpha_scale=self.dynamic_alpha_scale, beta_scale=self.dynamic_beta_scale)
+
+
+HC_KEYS = ("gamma", "dyn_alpha", "dyn_beta", "static_alpha", "static_beta", "alpha_scale", "beta_scale")
+
+
+# ----------------------------------------------------------------------------------------------
+# bf16 operand cache
+# ----------------------------------------------------------------------------------------------
+class _PackedWeights:
+    """bf16 (zero-padded) GEMM operand copies of fp32 parameters, refreshed when `_version` moves."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, key, params, build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            val = build()
+        self._cache[key] = (ver, val)
+        return val
+
+
+def pack_plain(w):
+    """[N, K] fp32 -> bf16 [N, pad8(K)]."""
+    return ops.cast_pad(w.detach(), _pad8(w.shape[1]))
+
+
+def pack_w1(w, inner):
+    """FeedForward W1 [2*inner, d]: a-rows then gate-rows, each block padded to a multiple of 8 rows."""
+    ip = _pad8(inner)
+    out = torch.zeros(2 * ip, w.shape[1], device=w.device, dtype=bf16)
+    ops.cast_pad(w.detach()[:inner], out=out[:inner])
+    ops.cast_pad(w.detach()[inner:], out=out[ip:ip + inner])
+    return out
+
+
+def best_split_k(M, N, K, n_sm=148):
+    """split-K factor for weight-gradient GEMMs (few output tiles, very long K)."""
+    bn = 64 if N <= 64 else (128 if N <= 128 or (-N) % 256 > (-N) % 128 else 256)
+    tiles = -(-M // 128) * -(-N // bn)
+    kb = -(-K // 64)
+    best, best_t = 1, None
+    for s in range(1, min(64, kb) + 1):
+        t = -(-tiles * s // n_sm) * (-(-kb // s) + 6)  # +6: pipeline fill / epilogue per tile
+        if best_t is None or t < best_t:
+            best, best_t = s, t
+    return best
+
+
+def wgrad(dy, x, out):
+    """out[N, K] (fp32, zero-initialised or accumulating) += dy[M, N]^T x[M, K]."""
+    Mtok = dy.shape[0]
+    s = best_split_k(dy.shape[1], x.shape[1], Mtok)
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, acc_mode=2 if s > 1 else 1, split_k=s)
+
+
+# ----------------------------------------------------------------------------------------------
+# the stack
+# ----------------------------------------------------------------------------------------------
+class _StackFn(torch.autograd.Function):
+    """Whole Transformer stack as one autograd node: explicit forward + backward over C-ABI kernels."""
+
+    @staticmethod
+    def forward(ctx, tr, x, mask, *params):
+        out, saved = tr._run_forward(x, mask, save=any(ctx.needs_input_grad))
+        ctx.tr = tr
+        ctx.saved = saved
+        kv = saved["kv"]
+        ctx.mark_non_differentiable(kv)
+        return out, kv
+
+    @staticmethod
+    def backward(ctx, dout, _dkv):
+        tr = ctx.tr
+        dx, grads = tr._run_backward(ctx.saved, dout)
+        ctx.saved = None
+        return (None, dx, None, *grads)
+
+
+class Transformer(nn.Module):
+    """audiolm_pytorch.py:410-560 (self-attention stack with hyper-connections and value residual)."""
+
+    def __init__(self, *, dim, depth, heads, dim_context=None, cross_attend=False, attn_dropout=0.0,
+                 ff_dropout=0.0, grad_shrink_alpha=0.1, cond_as_self_attn_prefix=False, rel_pos_bias=True,
+                 flash_attn=False, add_value_residual=True, num_residual_streams=4, **kwargs):
+        super().__init__()
+        rel_pos_bias = rel_pos_bias and not flash_attn
+        if cross_attend or cond_as_self_attn_prefix:
+            raise NotImplementedError("text / audio conditioning is outside the accelerated hot path")
+        if num_residual_streams != 4:
+            raise NotImplementedError("hyper-connection kernels are built for num_residual_streams=4")
+        if attn_dropout != 0.0 or ff_dropout != 0.0:
+            raise NotImplementedError("dropout > 0 is not built (reference default is 0)")
+        if dim % 8 != 0:
+            raise ValueError("dim must be a multiple of 8")
+        self.dim = dim
+        self.depth = depth
+        self.heads = heads
+        self.dim_context = default(dim_context, dim)
+        self.cond_as_self_attn_prefix = False
+        self.grad_shrink_alpha = grad_shrink_alpha
+        self.num_residual_streams = num_residual_streams
+        self.add_value_residual = add_value_residual
+        self.rel_pos_bias = None
+        self._wants_rel_pos_bias = rel_pos_bias
+
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                HyperConnections(num_residual_streams, dim=dim,
+                                 branch=Attention(dim=dim, heads=heads, dropout=attn_dropout, flash=flash_attn,
+                                                  causal=True, **kwargs)),
+                None,
+                HyperConnections(num_residual_streams, dim=dim, branch=FeedForward(dim=dim, dropout=ff_dropout)),
+            ]))
+        self.norm = LayerNorm(dim)
+        self._packed = _PackedWeights()
+
+    # ---- parameter plumbing ------------------------------------------------------------------
+    def _param_list(self):
+        ps = []
+        for attn_hc, _, ff_hc in self.layers:
+            a, f = attn_hc.branch, ff_hc.branch
+            ps += [*attn_hc.kernel_params().values(), a.norm.gamma, a.to_q.weight, a.to_kv.weight,
+                   a.to_out[0].weight]
+            ps += [*ff_hc.kernel_params().values(), getattr(f, "0").gamma, getattr(f, "1").weight,
+                   getattr(f, "3").gamma, getattr(f, "5").weight]
+        ps.append(self.norm.gamma)
+        return ps
+
+    PER_LAYER = 2 * len(HC_KEYS) + 4 + 4
+
+    def _weights(self, i):
+        attn_hc, _, ff_hc = self.layers[i]
+        a, f = attn_hc.branch, ff_hc.branch
+        pk = self._packed
+        w1 = getattr(f, "1").weight
+        w2 = getattr(f, "5").weight
+        return dict(
+            wq=pk.get((i, "q"), [a.to_q.weight], lambda: pack_plain(a.to_q.weight)),
+            wkv=pk.get((i, "kv"), [a.to_kv.weight], lambda: pack_plain(a.to_kv.weight)),
+            wo=pk.get((i, "o"), [a.to_out[0].weight], lambda: pack_plain(a.to_out[0].weight)),
+            w1=pk.get((i, "w1"), [w1], lambda: pack_w1(w1, f.inner)),
+            w2=pk.get((i, "w2"), [w2], lambda: pack_plain(w2)),
+        )
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, x, self_attn_mask=None, context=None, context_mask=None, attn_bias=None,
+                return_kv_cache=False, kv_cache=None):
+        if exists(context):
+            raise NotImplementedError("conditioning context is outside the accelerated hot path")
+        if exists(attn_bias) or self._wants_rel_pos_bias:
+            raise NotImplementedError(
+                "relative-position / additive attention bias (flash_attn=False path) is not built yet; "
+                "construct the transformer with flash_attn=True")
+        if not x.is_cuda:
+            raise ops._lib.AlmError("Transformer needs CUDA tensors (no CPU fallback)")
+        if exists(kv_cache):
+            out, kv = self._forward_cached(x, self_attn_mask, kv_cache)
+        else:
+            out, kv = _StackFn.apply(self, x, self_attn_mask, *self._param_list())
+        if not return_kv_cache:
+            return out
+        return out, kv
+
+    def _run_forward(self, x, mask, save):
+        b, n, d = x.shape
+        M = b * n
+        H = self.heads
+        x2 = x.detach().reshape(M, d).to(f32).contiguous()
+        mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        L = []
+        hc0 = self.layers[0][0]
+        R, bin_, xn, beta, aux = ops.hc_pre_fwd(hc0.kernel_params(), hc0.branch.norm.gamma, x_expand=x2, M=M, d=d)
+        v_first = None
+        kvs = []
+        for i, (attn_hc, _, ff_hc) in enumerate(self.layers):
+            W = self._weights(i)
+            f = ff_hc.branch
+            inner, ip = f.inner, _pad8(f.inner)
+            rec = dict(R_a=R, bin_a=bin_, xn_a=xn, beta_a=beta, aux_a=aux)
+            q = ops.gemm(xn, W["wq"])                      # [M, H*64]
+            kv = ops.gemm(bin_, W["wkv"])                  # [M, 128]  (k | v) from the UN-normalised input
+            if self.add_value_residual and v_first is not None:
+                ops.axpby(kv[:, 64:], 0.5, v_first, 0.5, out=kv[:, 64:])
+            elif self.add_value_residual:
+                v_first = kv[:, 64:].clone()               # layer-0 values before any mixing (:355-358)
+            k3 = kv[:, :64].unflatten(0, (b, n))
+            v3 = kv[:, 64:].unflatten(0, (b, n))
+            o, lse = ops.mqa_attn_fwd(q.view(b, n, H * 64), k3, v3, heads=H, key_mask=mask_u8, causal=True)
+            o2 = o.view(M, H * 64)
+            Y = ops.gemm(o2, W["wo"])
+            rec.update(q=q, kv=kv, o=o2, lse=lse, Y_a=Y)
+            kvs.append(kv)
+            R2, bin2, xn2, beta2, aux2 = ops.hc_pre_fwd(ff_hc.kernel_params(), getattr(f, "0").gamma, R_in=R, Y=Y,
+                                                        beta_prev=beta, M=M, d=d)
+            h = ops.gemm(xn2, W["w1"])                     # [M, 2*ip]
+            gn, st = ops.geglu_ln_fwd(h, getattr(f, "3").gamma, inner=inner, inner_pad=ip)
+            Y2 = ops.gemm(gn, W["w2"])
+            rec.update(R_f=R2, xn_f=xn2, beta_f=beta2, aux_f=aux2, h=h, gn=gn, st=st, Y_f=Y2)
+            L.append(rec)
+            if i + 1 < self.depth:
+                nxt = self.layers[i + 1][0]
+                R, bin_, xn, beta, aux = ops.hc_pre_fwd(nxt.kernel_params(), nxt.branch.norm.gamma, R_in=R2, Y=Y2,
+                                                        beta_prev=beta2, M=M, d=d)
+        last = L[-1]
+        out, stats = ops.hc_post_fwd(last["R_f"], last["Y_f"], last["beta_f"], self.norm.gamma, M=M, d=d)
+        # kv cache tensor [depth, 2, b, n, 64] as the reference returns it (audiolm_pytorch.py:370, 560)
+        kv_t = torch.stack([kv.view(b, n, 2, 64).permute(2, 0, 1, 3) for kv in kvs])
+        saved = dict(kv=kv_t)
+        if save:
+            saved.update(L=L, x2=x2, mask=mask_u8, stats=stats, shape=(b, n, d), x_dtype=x.dtype)
+        return out.view(b, n, d), saved
+
+    # ---- backward ------------------------------------------------------------------------------
+    def _run_backward(self, S, dout):
+        b, n, d = S["shape"]
+        M = b * n
+        H = self.heads
+        dev = dout.device
+        L = S["L"]
+        dout = dout.reshape(M, d).to(bf16).contiguous()
+        params = self._param_list()
+        grads = [torch.zeros_like(p, dtype=f32) for p in params]
+        PL = self.PER_LAYER
+        nk = len(HC_KEYS)
+
+        def slot(i):
+            g = grads[i * PL:(i + 1) * PL]
+            a_hc = dict(zip(HC_KEYS, g[:nk]))
+            g_ln_a, g_wq, g_wkv, g_wo = g[nk:nk + 4]
+            f_hc = dict(zip(HC_KEYS, g[nk + 4:2 * nk + 4]))
+            g_ln_f, g_w1, g_ln2, g_w2 = g[2 * nk + 4:]
+            return a_hc, g_ln_a, g_wq, g_wkv, g_wo, f_hc, g_ln_f, g_w1, g_ln2, g_w2
+
+        last = L[-1]
+        dR, dY, dbeta = ops.hc_post_bwd(last["R_f"], last["Y_f"], last["beta_f"], self.norm.gamma, S["stats"], dout,
+                                        grads[-1], M=M, d=d)
+        dv_first = None
+        dx = None
+        for i in reversed(range(self.depth)):
+            attn_hc, _, ff_hc = self.layers[i]
+            a, f = attn_hc.branch, ff_hc.branch
+            inner, ip = f.inner, _pad8(f.inner)
+            W = self._weights(i)
+            rec = L[i]
+            a_hc, g_ln_a, g_wq, g_wkv, g_wo, f_hc, g_ln_f, g_w1, g_ln2, g_w2 = slot(i)
+            # ---- feed-forward branch ----
+            dgn = ops.gemm(dY, W["w2"], b_mn=True)                       # [M, ip]
+            _wgrad_cols(dY, rec["gn"], g_w2, inner)
+            dh = ops.geglu_ln_bwd(rec["h"], getattr(f, "3").gamma, rec["st"], dgn, g_ln2, inner=inner, inner_pad=ip)
+            dxn_f = ops.gemm(dh, W["w1"], b_mn=True)                     # [M, d]
+            wgrad(dh[:, :inner], rec["xn_f"], g_w1[:inner])
+            wgrad(dh[:, ip:ip + inner], rec["xn_f"], g_w1[inner:])
+            dR_a, dY_a, dbeta_a = ops.hc_pre_bwd(ff_hc.kernel_params(), getattr(f, "0").gamma, f_hc, g_ln_f,
+                                                 rec["aux_f"], dR, dxn_f, dbeta, R_in=rec["R_a"], Y=rec["Y_a"],
+                                                 beta_prev=rec["beta_a"], M=M, d=d)
+            # ---- attention branch ----
+            dO = ops.gemm(dY_a, W["wo"], b_mn=True)                      # [M, H*64]
+            wgrad(dY_a, rec["o"], g_wo)
+            kv = rec["kv"]
+            k3 = kv[:, :64].unflatten(0, (b, n))
+            v3 = kv[:, 64:].unflatten(0, (b, n))
+            dq, dk, dv = ops.mqa_attn_bwd(rec["q"].view(b, n, H * 64), k3, v3, rec["o"].view(b, n, H * 64),
+                                          dO.view(b, n, H * 64), rec["lse"], heads=H, key_mask=S["mask"], causal=True)
+            dkv = torch.empty(M, 128, device=dev, dtype=bf16)
+            ops.axpby(dk.view(M, 64), 1.0, None, 0.0, out=dkv[:, :64])
+            dv2 = dv.view(M, 64)
+            if self.add_value_residual and i > 0:
+                ops.axpby(dv2, 0.5, None, 0.0, out=dkv[:, 64:])
+                dv_first = ops.axpby(dv2, 0.5, dv_first, 1.0) if dv_first is not None else ops.axpby(dv2, 0.5, None, 0.0)
+            elif self.add_value_residual and dv_first is not None:
+                ops.axpby(dv2, 1.0, dv_first, 1.0, out=dkv[:, 64:])
+            else:
+                ops.axpby(dv2, 1.0, None, 0.0, out=dkv[:, 64:])
+            dq2 = dq.view(M, H * 64)
+            dxn_a = ops.gemm(dq2, W["wq"], b_mn=True)
+            dbin_a = ops.gemm(dkv, W["wkv"], b_mn=True)
+            wgrad(dq2, rec["xn_a"], g_wq)
+            wgrad(dkv, rec["bin_a"], g_wkv)
+            if i > 0:
+                prev = L[i - 1]
+                dR, dY, dbeta = ops.hc_pre_bwd(attn_hc.kernel_params(), a.norm.gamma, a_hc, g_ln_a, rec["aux_a"], dR_a,
+                                               dxn_a, dbeta_a, dbin_extra=dbin_a, R_in=prev["R_f"], Y=prev["Y_f"],
+                                               beta_prev=prev["beta_f"], M=M, d=d)
+            else:
+                dx = ops.hc_pre_bwd(attn_hc.kernel_params(), a.norm.gamma, a_hc, g_ln_a, rec["aux_a"], dR_a, dxn_a,
+                                    dbeta_a, dbin_extra=dbin_a, x_expand=S["x2"], dx_scale=self.grad_shrink_alpha,
+                                    M=M, d=d)
+        return dx.view(b, n, d).to(S["x_dtype"]), grads
+
+    # ---- incremental (KV-cache) inference ------------------------------------------------------
+    @torch.no_grad()
+    def _forward_cached(self, x, mask, kv_cache):
+        """x is the FULL sequence; only x[:, cache_len:] is processed (audiolm_pytorch.py:489-496)."""
+        cache_len = kv_cache.shape[-2]
+        x = x[:, cache_len:]
+        b, n, d = x.shape
+        M = b * n
+        H = self.heads
+        x2 = x.reshape(M, d).to(f32).contiguous()
+        mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        hc0 = self.layers[0][0]
+        R, bin_, xn, beta, _ = ops.hc_pre_fwd(hc0.kernel_params(), hc0.branch.norm.gamma, x_expand=x2, M=M, d=d)
+        v_first = None
+        new_cache = []
+        for i, (attn_hc, _, ff_hc) in enumerate(self.layers):
+            W = self._weights(i)
+            f = ff_hc.branch
+            inner, ip = f.inner, _pad8(f.inner)
+            q = ops.gemm(xn, W["wq"])
+            kv = ops.gemm(bin_, W["wkv"])
+            if self.add_value_residual and v_first is not None:
+                ops.axpby(kv[:, 64:], 0.5, v_first, 0.5, out=kv[:, 64:])
+            elif self.add_value_residual:
+                v_first = kv[:, 64:].clone()
+            ck, cv = kv_cache[i][0].to(bf16), kv_cache[i][1].to(bf16)
+            k_all = torch.cat((ck, kv[:, :64].unflatten(0, (b, n))), dim=1).contiguous()
+            v_all = torch.cat((cv, kv[:, 64:].unflatten(0, (b, n))), dim=1).contiguous()
+            new_cache.append(torch.stack((k_all, v_all)))
+            o, _ = ops.mqa_attn_fwd(q.view(b, n, H * 64), k_all, v_all, heads=H, key_mask=mask_u8, causal=True,
+                                    return_lse=False)
+            Y = ops.gemm(o.view(M, H * 64), W["wo"])
+            R2, _, xn2, beta2, _ = ops.hc_pre_fwd(ff_hc.kernel_params(), getattr(f, "0").gamma, R_in=R, Y=Y,
+                                                  beta_prev=beta, M=M, d=d)
+            h = ops.gemm(xn2, W["w1"])
+            gn, _ = ops.geglu_ln_fwd(h, getattr(f, "3").gamma, inner=inner, inner_pad=ip)
+            Y2 = ops.gemm(gn, W["w2"])
+            if i + 1 < self.depth:
+                nxt = self.layers[i + 1][0]
+                R, bin_, xn, beta, _ = ops.hc_pre_fwd(nxt.kernel_params(), nxt.branch.norm.gamma, R_in=R2, Y=Y2,
+                                                      beta_prev=beta2, M=M, d=d)
+        out, _ = ops.hc_post_fwd(R2, Y2, beta2, self.norm.gamma, M=M, d=d)
+        return out.view(b, n, d), torch.stack(new_cache)
+
+
+def _wgrad_cols(dy, x_padded, out, cols):
+    """weight gradient when the activation operand carries zero padding columns: out [N, cols]."""
+    Mtok = dy.shape[0]
+    s = best_split_k(dy.shape[1], cols, Mtok)
+    ops.gemm(dy, x_padded[:, :cols], a_mn=True, b_mn=True, out=out, acc_mode=2 if s > 1 else 1, split_k=s)
