@@ -1,0 +1,72 @@
+"""CPU: drop-in surface — constructor kwargs, state_dict keys/shapes, C-ABI symbols, host-side helpers."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+G = ROOT / "tests" / "golden"
+
+
+def load(name):
+    return torch.load(G / name, map_location="cpu", weights_only=False)
+
+
+@pytest.mark.parametrize("fixture,cls_name", [("semantic.pt", "SemanticTransformer"), ("coarse.pt", "CoarseTransformer"),
+                                              ("fine.pt", "FineTransformer")])
+def test_state_dict_keys_match_reference(fixture, cls_name):
+    from audiolm_pytorch_b200 import audiolm
+
+    g = load(fixture)
+    m = getattr(audiolm, cls_name)(**g["kwargs"])
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in g["state"].items()}
+    assert mine == ref
+    m.load_state_dict(g["state"], strict=True)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib_path = ROOT / "audiolm_pytorch_b200" / "libalm_b200.so"
+    if not lib_path.exists():
+        from audiolm_pytorch_b200 import build
+
+        build.build()
+    lib = ctypes.CDLL(str(lib_path))
+    header = (ROOT / "include" / "alm_b200.h").read_text()
+    names = set(re.findall(r"\b(alm_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 15
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/alm_b200.h but not exported"
+    from audiolm_pytorch_b200 import _lib
+
+    for n in _lib.SIGNATURES:
+        assert n in names, f"{n} bound in _lib.py but not declared in the header"
+    assert lib.alm_version() >= 100
+
+
+def test_ops_refuse_cpu_tensors():
+    from audiolm_pytorch_b200 import _lib, ops
+
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(_lib.AlmError):
+        ops.gemm(a, a)
+
+
+def test_fcm_mask_and_eos_helpers():
+    from audiolm_pytorch_b200 import heads
+
+    m = heads.generate_mask_with_prob((4, 100), 0.15, "cpu")
+    assert m[:, 0].all() and (~m).sum(-1).eq(15).all()
+    g = load("sampling.pt")
+    assert torch.equal(heads.top_k(g["logits"], thres=0.9), g["filtered"])
+    assert torch.equal(heads.mask_out_after_eos_id(g["seq"], 64, keep_eos=False), g["seq_masked"])
+
+
+def test_split_k_heuristic_bounds():
+    from audiolm_pytorch_b200.transformer import best_split_k
+
+    for (M, N, K) in [(512, 1024, 32768), (128, 1024, 32768), (5460, 1024, 32768), (1024, 2730, 32768), (64, 64, 64)]:
+        s = best_split_k(M, N, K)
+        assert 1 <= s <= max(1, -(-K // 64))

@@ -1,0 +1,143 @@
+"""B200: the product transformers (CUDA kernels through the C ABI) vs goldens produced by the real reference."""
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).parent / "golden"
+DEV = "cuda"
+
+
+def load(name):
+    return torch.load(G / name, map_location="cpu", weights_only=False)
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
+
+
+TOL = 3e-2   # bf16 activations / fp32 accumulation vs the fp32 reference ("within 1e-2 rel" is checked as RMS below)
+
+
+def rms_rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-12)).item()
+
+
+def build(cls, g):
+    m = cls(**g["kwargs"])
+    m.load_state_dict(g["state"], strict=True)
+    return m.to(DEV)
+
+
+def test_semantic_forward_cache_loss_grads():
+    from audiolm_pytorch_b200.audiolm import SemanticTransformer, SemanticTransformerWrapper
+
+    g = load("semantic.pt")
+    m = build(SemanticTransformer, g).eval()
+    ids = g["ids"].to(DEV)
+    with torch.no_grad():
+        logits = m(ids=ids)
+        masked = m(ids=ids, self_attn_mask=g["mask"].to(DEV))
+        l12, cache = m(ids=ids[:, :12], return_kv_cache=True)
+        inc, _ = m(ids=ids, kv_cache=cache, return_kv_cache=True)
+    assert rms_rel(logits, g["logits"]) < 1e-2 and rel(logits, g["logits"]) < TOL
+    assert rms_rel(masked, g["logits_masked"]) < 1e-2
+    assert rel(cache, g["cache12"]) < TOL
+    assert rms_rel(inc, g["logits_inc"]) < 1.5e-2
+    w = SemanticTransformerWrapper(transformer=m, unique_consecutive=False, mask_prob=0.0).train()
+    loss = w(semantic_token_ids=ids, return_loss=True)
+    assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
+    loss.backward()
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, gr in g["grads"].items():
+        assert named[k].grad is not None, k
+        e = rms_rel(named[k].grad, gr)
+        worst = max(worst, e)
+        assert e < 6e-2, (k, e)
+    print("semantic worst grad rms rel err", worst)
+
+
+def test_coarse_forward_cache_loss_grads():
+    from audiolm_pytorch_b200.audiolm import CoarseTransformer, CoarseTransformerWrapper
+
+    g = load("coarse.pt")
+    m = build(CoarseTransformer, g).eval()
+    sem, coarse = g["sem"].to(DEV), g["coarse"].to(DEV)
+    with torch.no_grad():
+        sl, cl = m(semantic_token_ids=sem, coarse_token_ids=coarse)
+        slm, clm = m(semantic_token_ids=sem, coarse_token_ids=coarse, self_attn_mask=g["mask"].to(DEV))
+        (_, _), (kv_a, emb_a) = m(semantic_token_ids=sem, coarse_token_ids=coarse[:, :9], return_cache=True,
+                                   return_only_coarse_logits=True)
+        (_, cb), _ = m(semantic_token_ids=sem, coarse_token_ids=coarse[:, :10], return_cache=True, kv_cache=kv_a,
+                       embed_cache=emb_a, return_only_coarse_logits=True)
+    assert rms_rel(sl, g["sem_logits"]) < 1e-2 and rms_rel(cl, g["coarse_logits"]) < 1e-2
+    assert rms_rel(slm, g["sem_logits_masked"]) < 1e-2 and rms_rel(clm, g["coarse_logits_masked"]) < 1e-2
+    assert rel(kv_a, g["kv_a"]) < TOL and rms_rel(emb_a, g["emb_a"]) < 1e-2
+    assert rms_rel(cb, g["coarse_logits_b"]) < 1.5e-2
+
+    class _Codec:  # the wrapper constructor only reads rq_groups
+        rq_groups = 1
+
+    w = CoarseTransformerWrapper(transformer=m, codec=_Codec(), unique_consecutive=False, mask_prob=0.0).train()
+    loss = w(semantic_token_ids=sem, coarse_token_ids=coarse[:, :21], return_loss=True)
+    assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
+    loss.backward()
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, gr in g["grads"].items():
+        assert named[k].grad is not None, k
+        e = rms_rel(named[k].grad, gr)
+        worst = max(worst, e)
+        assert e < 6e-2, (k, e)
+    print("coarse worst grad rms rel err", worst)
+
+
+def test_fine_forward():
+    from audiolm_pytorch_b200.audiolm import FineTransformer
+
+    g = load("fine.pt")
+    m = build(FineTransformer, g).eval()
+    with torch.no_grad():
+        cl, fl = m(coarse_token_ids=g["coarse"].to(DEV), fine_token_ids=g["fine"].to(DEV))
+    assert rms_rel(cl, g["coarse_logits"]) < 1e-2 and rms_rel(fl, g["fine_logits"]) < 1e-2
+
+
+def test_matches_oracle_at_larger_size():
+    """seeded random weights, seq 384 / dim 256 / depth 3: CUDA path vs the CPU oracle restatement."""
+    from audiolm_pytorch_b200.audiolm import CoarseTransformer
+    from oracle import transformer as ot
+
+    torch.manual_seed(5)
+    kw = dict(num_semantic_tokens=100, codebook_size=128, num_coarse_quantizers=3, dim=256, depth=3, heads=4,
+              flash_attn=True)
+    m = CoarseTransformer(**kw)
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "dynamic_alpha_fn" in n_ or "dynamic_beta_fn" in n_:
+                p.normal_(0, 0.02)
+            if "logit_weights" in n_:
+                p.mul_(0.1)
+    st = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sem = torch.randint(0, 100, (2, 90))
+    coarse = torch.randint(0, 128, (2, 292))
+    (osl, ocl), _ = ot.coarse_forward(st, sem, coarse, heads=4, depth=3, codebook_size=128, num_coarse_quantizers=3)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        sl, cl = m(semantic_token_ids=sem.to(DEV), coarse_token_ids=coarse.to(DEV))
+    assert rms_rel(sl, osl) < 1e-2 and rms_rel(cl, ocl) < 1e-2
+
+
+def test_sampling_helpers_bit_exact():
+    from audiolm_pytorch_b200 import heads
+
+    g = load("sampling.pt")
+    filt = heads.top_k(g["logits"].to(DEV), thres=0.9)
+    assert torch.equal(filt.cpu(), g["filtered"])
+    noise = g["uniform"].to(DEV)
+    gum = -torch.log(-torch.log(noise + 1e-20) + 1e-20)
+    assert torch.equal((filt + gum).argmax(-1).cpu(), g["ids"])
+    assert torch.equal(heads.mask_out_after_eos_id(g["seq"].to(DEV), 64, keep_eos=False).cpu(), g["seq_masked"])
