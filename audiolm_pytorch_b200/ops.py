@@ -13,6 +13,46 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 
 
+# ---- optional in-stream kernel timing (bench.py roofline): CUDA events bracket each tagged launch -----
+_PROFILE = None
+
+
+def profile_start():
+    """begin collecting (start_event, end_event, work) tuples per kernel class on the current stream."""
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """-> {cls: (total_ms, total_work, launches)}; synchronises the device."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for cls, recs in (prof or {}).items():
+        ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        out[cls] = (ms, sum(w for _, _, w in recs), len(recs))
+    return out
+
+
+class _timed:
+    def __init__(self, cls, work):
+        self.cls, self.work = cls, work
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.b.record()
+            _PROFILE.setdefault(self.cls, []).append((self.a, self.b, self.work))
+        return False
+
+
 def _check_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -54,13 +94,14 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, alpha=1.0, b
     assert o3.dtype in (bf16, f32)
     if bias is not None:
         assert bias.dtype == f32 and bias.numel() == N and bias.is_contiguous()
-    _lib.call(
-        "alm_gemm_bf16",
-        a3, int(a_mn), a3.stride(1), a3.stride(0) if nb > 1 else 0,
-        b3, int(b_mn), b3.stride(1), b3.stride(0) if nb > 1 else 0,
-        o3, int(o3.dtype == f32), o3.stride(1), o3.stride(0) if nb > 1 else 0,
-        M, N, K, nb, float(alpha), bias, int(acc_mode), int(split_k),
-    )
+    with _timed("gemm_bf16_tcgen05", 2.0 * M * N * K * nb):
+        _lib.call(
+            "alm_gemm_bf16",
+            a3, int(a_mn), a3.stride(1), a3.stride(0) if nb > 1 else 0,
+            b3, int(b_mn), b3.stride(1), b3.stride(0) if nb > 1 else 0,
+            o3, int(o3.dtype == f32), o3.stride(1), o3.stride(0) if nb > 1 else 0,
+            M, N, K, nb, float(alpha), bias, int(acc_mode), int(split_k),
+        )
     return out
 
 
@@ -87,11 +128,14 @@ def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, retu
         assert key_mask.shape == (b, n_k)
     if scale is None:
         scale = 64 ** -0.5
-    _lib.call(
-        "alm_mqa_attn_fwd",
-        q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), key_mask,
-        o, o.stride(1), lse, n_q_pad, b, heads, n_q, n_k, int(causal), float(scale),
-    )
+    # algorithmic FLOPs: QK^T + PV over the visible (lower-triangle) part only
+    vis = (n_q * n_k - n_q * (n_q - 1) / 2) if causal else n_q * n_k
+    with _timed("mqa_attn_fwd_tcgen05", 4.0 * b * heads * 64 * vis):
+        _lib.call(
+            "alm_mqa_attn_fwd",
+            q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), key_mask,
+            o, o.stride(1), lse, n_q_pad, b, heads, n_q, n_k, int(causal), float(scale),
+        )
     return o, lse
 
 
@@ -115,12 +159,14 @@ def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, sca
     dq = torch.empty(b, n_q, hd, device=q.device, dtype=bf16)
     dk = torch.empty(b, n_k, 64, device=q.device, dtype=bf16)
     dv = torch.empty(b, n_k, 64, device=q.device, dtype=bf16)
-    _lib.call(
-        "alm_mqa_attn_bwd",
-        q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), d_o, d_o.stride(1), key_mask,
-        lse, delta, n_q_pad, dq, dq.stride(1), dk, dk.stride(1), dv, dv.stride(1),
-        b, heads, n_q, n_k, int(causal), float(scale),
-    )
+    vis = (n_q * n_k - n_q * (n_q - 1) / 2) if causal else n_q * n_k
+    with _timed("mqa_attn_bwd_tcgen05", 10.0 * b * heads * 64 * vis):  # 5 matmuls (algorithmic; 7 executed)
+        _lib.call(
+            "alm_mqa_attn_bwd",
+            q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), d_o, d_o.stride(1), key_mask,
+            lse, delta, n_q_pad, dq, dq.stride(1), dk, dk.stride(1), dv, dv.stride(1),
+            b, heads, n_q, n_k, int(causal), float(scale),
+        )
     return dq, dk, dv
 
 

@@ -1,0 +1,50 @@
+"""Data-parallel gradient exchange for the transformer trainers: ONE flat fp32 bucket, ONE all-reduce.
+
+The reference reaches the same collective through accelerate -> torch DDP (trainer.py:75, 396, 834, 1136,
+1432: `accelerator.prepare`, and the reducer hooks fired by `accelerator.backward`, :580, 949, 1247, 1548)
+with 25 MB buckets and `find_unused_parameters=True`.  Here every parameter's `.grad` is a view into one
+contiguous buffer, so the whole exchange is a single NCCL all-reduce over NVLink / NVSwitch followed by
+a scale by 1/world (mean, as DDP does).  Works on CPU with gloo for the world_size-2 tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBucket:
+    def __init__(self, params, dtype=torch.float32):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=dtype)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None, async_op=False):
+        """sum over ranks then divide by world size (DDP semantics).  Returns the work handle if async."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        world = dist.get_world_size(group)
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if async_op:
+            return work
+        self.flat.div_(world)
+        return None
+
+    def grad_norm(self):
+        return self.flat.norm(2)
+
+    def clip_grad_norm_(self, max_norm):
+        """global L2 clip over the flat bucket (accelerator.clip_grad_norm_, trainer.py:596, 954, 1252, 1553)."""
+        norm = self.grad_norm()
+        scale = (max_norm / (norm + 1e-6)).clamp(max=1.0)
+        self.flat.mul_(scale)
+        return norm
