@@ -283,3 +283,66 @@ def cast_pad(src, cols_pad=None, out=None):
 def scale_by_scalar(x, s):
     _lib.call("alm_scale_by_scalar_bf16", x, s, x.numel())
     return x
+
+
+# ---- SoundStream codec -------------------------------------------------------------------------------
+PAD_MODES = {"reflect": 0, "constant": 1, "zeros": 1, "replicate": 2}
+
+
+def causal_conv1d(x, weight, bias=None, *, stride=1, dilation=1, pad_mode="reflect", elu=False, residual=None):
+    """CausalConv1d forward (soundstream.py:332-345) with optional fused ELU and skip add. fp32 [B,C,T]."""
+    _check_cuda(x, weight, bias, residual)
+    assert x.dtype == f32 and weight.dtype == f32
+    x = x.contiguous()
+    B, Cin, T = x.shape
+    Cout, Cin_w, K = weight.shape
+    assert Cin_w == Cin, "groups != 1 is not supported"
+    pad = dilation * (K - 1) + 1 - stride
+    Tout = (T + pad - dilation * (K - 1) - 1) // stride + 1
+    y = torch.empty(B, Cout, Tout, device=x.device, dtype=f32)
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == y.shape
+    _lib.call("alm_causal_conv1d_fwd", x, weight.contiguous(), None if bias is None else bias.contiguous(), residual,
+              y, B, Cin, Cout, T, K, stride, dilation, PAD_MODES[pad_mode], int(elu))
+    return y
+
+
+def causal_conv_transpose1d(x, weight, bias=None, *, stride):
+    """CausalConvTranspose1d forward (soundstream.py:347-360): weight [Cin, Cout, 2*stride]."""
+    _check_cuda(x, weight, bias)
+    x = x.contiguous()
+    B, Cin, n = x.shape
+    Cin_w, Cout, K = weight.shape
+    assert Cin_w == Cin and K == 2 * stride
+    y = torch.empty(B, Cout, n * stride, device=x.device, dtype=f32)
+    _lib.call("alm_causal_convT1d_fwd", x, weight.contiguous(), None if bias is None else bias.contiguous(), y, B,
+              Cin, Cout, n, stride)
+    return y
+
+
+def rvq_encode(x, codebooks):
+    """x [N, D] fp32, codebooks [Q, C, D] fp32 -> (quantized [N, D] fp32, indices [N, Q] int64)."""
+    _check_cuda(x, codebooks)
+    assert x.dtype == f32 and codebooks.dtype == f32 and x.stride(-1) == 1
+    N, D = x.shape
+    Q, C, D2 = codebooks.shape
+    assert D == D2
+    codebooks = codebooks.contiguous()
+    quant = torch.empty(N, D, device=x.device, dtype=f32)
+    idx = torch.empty(N, Q, device=x.device, dtype=torch.int64)
+    ws = torch.empty(Q * C, device=x.device, dtype=f32)
+    _lib.call("alm_rvq_encode", x, x.stride(0), codebooks, ws, quant, D, idx, Q, N, D, C, Q)
+    return quant, idx
+
+
+def rvq_decode(indices, codebooks):
+    """indices [N, Q] int64 (-1 = dropped) -> sum of selected codes [N, D] fp32."""
+    _check_cuda(indices, codebooks)
+    indices = indices.to(torch.int64).contiguous()
+    N, Q = indices.shape
+    Qc, C, D = codebooks.shape
+    assert Q <= Qc
+    out = torch.empty(N, D, device=indices.device, dtype=f32)
+    _lib.call("alm_rvq_decode", indices, Q, codebooks.contiguous(), out, D, N, D, C, Q)
+    return out

@@ -1,0 +1,297 @@
+"""SoundStream codec inference path on libalm_b200 (sm_100a): causal conv encoder -> residual VQ -> decoder.
+
+Drop-in surface of /root/reference/audiolm_pytorch/soundstream.py:314-395, 451-866 for the calls the AudioLM
+hot path makes: `forward(x, return_encoded=True | return_codes_only=True | return_recons_only=True)`,
+`tokenize`, `decode_from_codebook_indices`, `decode`, with the reference's constructor kwargs and
+state_dict keys for `encoder.*`, `decoder.*`, `rq.*`.  GAN / mel training losses, the local-attention
+bottleneck (use_local_attn=True), LFQ / FSQ quantizers and FiLM denoising are outside this build.
+"""
+from __future__ import annotations
+
+import functools
+import pickle
+from itertools import cycle
+from pathlib import Path
+
+import torch
+from torch import nn
+
+from . import ops
+
+f32 = torch.float32
+
+
+def exists(v):
+    return v is not None
+
+
+class CausalConv1d(nn.Module):
+    """soundstream.py:332-345; parameters live in `.conv` (nn.Conv1d) for state_dict compatibility."""
+
+    def __init__(self, chan_in, chan_out, kernel_size, pad_mode="reflect", **kwargs):
+        super().__init__()
+        self.dilation = kwargs.get("dilation", 1)
+        self.stride = kwargs.get("stride", 1)
+        self.pad_mode = pad_mode
+        self.causal_padding = self.dilation * (kernel_size - 1) + (1 - self.stride)
+        self.conv = nn.Conv1d(chan_in, chan_out, kernel_size, **kwargs)
+
+    def forward(self, x, elu=False, residual=None):
+        return ops.causal_conv1d(x, self.conv.weight, self.conv.bias, stride=self.stride, dilation=self.dilation,
+                                 pad_mode=self.pad_mode, elu=elu, residual=residual)
+
+
+class CausalConvTranspose1d(nn.Module):
+    """soundstream.py:347-360."""
+
+    def __init__(self, chan_in, chan_out, kernel_size, stride, **kwargs):
+        super().__init__()
+        assert kernel_size == 2 * stride
+        self.upsample_factor = stride
+        self.conv = nn.ConvTranspose1d(chan_in, chan_out, kernel_size, stride, **kwargs)
+
+    def forward(self, x):
+        return ops.causal_conv_transpose1d(x, self.conv.weight, self.conv.bias, stride=self.upsample_factor)
+
+
+class _RUBody(nn.Module):
+    """holds the two convs under the reference's Sequential indices 0 and 2 (1, 3 are ELUs)."""
+
+    def __init__(self, chan_in, chan_out, dilation, kernel_size, pad_mode):
+        super().__init__()
+        self.add_module("0", CausalConv1d(chan_in, chan_out, kernel_size, dilation=dilation, pad_mode=pad_mode))
+        self.add_module("2", CausalConv1d(chan_out, chan_out, 1, pad_mode=pad_mode))
+
+
+class ResidualUnit(nn.Module):
+    """x + ELU(conv1(ELU(conv7_dil(x)))) (soundstream.py:362-369) in two fused launches; keys `fn.{0,2}.conv.*`."""
+
+    def __init__(self, chan_in, chan_out, dilation, kernel_size=7, squeeze_excite=False, pad_mode="reflect"):
+        super().__init__()
+        if squeeze_excite:
+            raise NotImplementedError("squeeze_excite=True is not built")
+        self.fn = _RUBody(chan_in, chan_out, dilation, kernel_size, pad_mode)
+
+    def forward(self, x):
+        h = getattr(self.fn, "0")(x, elu=True)
+        return getattr(self.fn, "2")(h, elu=True, residual=x)
+
+
+def EncoderBlock(chan_in, chan_out, stride, cycle_dilations=(1, 3, 9), squeeze_excite=False, pad_mode="reflect"):
+    it = cycle(cycle_dilations)
+    return nn.Sequential(*[ResidualUnit(chan_in, chan_in, next(it), squeeze_excite=squeeze_excite, pad_mode=pad_mode)
+                           for _ in range(3)],
+                         CausalConv1d(chan_in, chan_out, 2 * stride, stride=stride))
+
+
+def DecoderBlock(chan_in, chan_out, stride, cycle_dilations=(1, 3, 9), squeeze_excite=False, pad_mode="reflect"):
+    it = cycle(cycle_dilations)
+    return nn.Sequential(CausalConvTranspose1d(chan_in, chan_out, 2 * stride, stride=stride),
+                         *[ResidualUnit(chan_out, chan_out, next(it), squeeze_excite=squeeze_excite, pad_mode=pad_mode)
+                           for _ in range(3)])
+
+
+# ---- residual VQ containers (state_dict keys of vector-quantize-pytorch) ---------------------------
+class _Codebook(nn.Module):
+    def __init__(self, dim, codebook_size):
+        super().__init__()
+        self.register_buffer("initted", torch.Tensor([False]))
+        self.register_buffer("cluster_size", torch.ones(1, codebook_size))
+        self.register_buffer("embed_avg", torch.zeros(1, codebook_size, dim))
+        self.register_buffer("embed", torch.zeros(1, codebook_size, dim))
+
+
+class _VQLayer(nn.Module):
+    def __init__(self, dim, codebook_size):
+        super().__init__()
+        self._codebook = _Codebook(dim, codebook_size)
+
+
+class ResidualVQ(nn.Module):
+    def __init__(self, *, dim, num_quantizers, codebook_size, **_):
+        super().__init__()
+        self.layers = nn.ModuleList([_VQLayer(dim, codebook_size) for _ in range(num_quantizers)])
+
+    def codebooks(self):
+        return torch.stack([l._codebook.embed[0] for l in self.layers]).to(f32)
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("RVQ training (EMA / k-means / commitment loss) is outside this build")
+        if not all(bool(l._codebook.initted.item()) for l in self.layers):
+            raise RuntimeError("codebooks are not initialised (load a checkpoint; k-means init is not built)")
+        b, n, d = x.shape
+        quant, idx = ops.rvq_encode(x.reshape(b * n, d).to(f32).contiguous(), self.codebooks())
+        return quant.view(b, n, d), idx.view(b, n, -1), torch.zeros(1, len(self.layers), device=x.device)
+
+    def get_output_from_indices(self, indices):
+        b, n, q = indices.shape
+        return ops.rvq_decode(indices.reshape(b * n, q), self.codebooks()).view(b, n, -1)
+
+
+class GroupedResidualVQ(nn.Module):
+    """channels split into `groups`, one ResidualVQ each (soundstream.py:592-607)."""
+
+    def __init__(self, *, dim, groups=1, **kwargs):
+        super().__init__()
+        assert dim % groups == 0
+        self.groups = groups
+        self.rvqs = nn.ModuleList([ResidualVQ(dim=dim // groups, **kwargs) for _ in range(groups)])
+
+    def forward(self, x):
+        outs = [rvq(c) for rvq, c in zip(self.rvqs, x.chunk(self.groups, dim=-1))]
+        return (torch.cat([o[0] for o in outs], dim=-1), torch.stack([o[1] for o in outs]),
+                torch.stack([o[2] for o in outs]))
+
+    def get_output_from_indices(self, indices):  # g b n q
+        return torch.cat([rvq.get_output_from_indices(i) for rvq, i in zip(self.rvqs, indices)], dim=-1)
+
+
+class SoundStream(nn.Module):
+    """soundstream.py:451-866 (inference path)."""
+
+    def __init__(self, *, channels=32, strides=(2, 4, 5, 8), channel_mults=(2, 4, 8, 16), codebook_dim=512,
+                 codebook_size=None, finite_scalar_quantizer_levels=None, rq_num_quantizers=8,
+                 rq_commitment_weight=1.0, rq_ema_decay=0.95, rq_quantize_dropout_multiple_of=1, rq_groups=1,
+                 rq_stochastic_sample_codes=False, rq_rotation_trick=True, rq_kwargs: dict = {},
+                 use_lookup_free_quantizer=False, use_finite_scalar_quantizer=False, input_channels=1,
+                 discr_multi_scales=(1, 0.5, 0.25), stft_normalized=False, enc_cycle_dilations=(1, 3, 9),
+                 dec_cycle_dilations=(1, 3, 9), multi_spectral_window_powers_of_two=tuple(range(6, 12)),
+                 multi_spectral_n_ffts=512, multi_spectral_n_mels=64, recon_loss_weight=1.0,
+                 multi_spectral_recon_loss_weight=1e-5, adversarial_loss_weight=1.0, feature_loss_weight=100,
+                 quantize_dropout_cutoff_index=1, target_sample_hz=16000, use_local_attn=True, attn_window_size=128,
+                 attn_dim_head=64, attn_heads=8, attn_depth=1, attn_xpos_scale_base=None,
+                 attn_dynamic_pos_bias=False, use_gate_loop_layers=False, squeeze_excite=False,
+                 complex_stft_discr_logits_abs=True, pad_mode="reflect", stft_discriminator=None,
+                 complex_stft_discr_kwargs: dict = dict()):
+        super().__init__()
+        cfg = dict(locals())
+        cfg.pop("self", None)
+        cfg.pop("__class__", None)
+        self._configs = pickle.dumps(cfg)
+        if use_local_attn:
+            raise NotImplementedError("the LocalMHA bottleneck (use_local_attn=True) is not built yet; "
+                                      "construct with use_local_attn=False")
+        if use_lookup_free_quantizer or use_finite_scalar_quantizer or use_gate_loop_layers:
+            raise NotImplementedError("LFQ / FSQ / gate-loop variants are outside this build")
+        assert exists(codebook_size)
+        self.target_sample_hz = target_sample_hz
+        self.single_channel = input_channels == 1
+        self.strides = strides
+        layer_channels = (channels, *[m * channels for m in channel_mults])
+        pairs = tuple(zip(layer_channels[:-1], layer_channels[1:]))
+        self.encoder = nn.Sequential(
+            CausalConv1d(input_channels, channels, 7, pad_mode=pad_mode),
+            *[EncoderBlock(ci, co, s, enc_cycle_dilations, squeeze_excite, pad_mode) for (ci, co), s in zip(pairs, strides)],
+            CausalConv1d(layer_channels[-1], codebook_dim, 3, pad_mode=pad_mode))
+        self.encoder_attn = None
+        self.decoder_attn = None
+        self.num_quantizers = rq_num_quantizers
+        self.codebook_dim = codebook_dim
+        self.codebook_size = codebook_size
+        self.rq_groups = rq_groups
+        self.use_lookup_free_quantizer = False
+        self.use_finite_scalar_quantizer = False
+        self.rq = GroupedResidualVQ(dim=codebook_dim, num_quantizers=rq_num_quantizers, codebook_size=codebook_size,
+                                    groups=rq_groups)
+        self.decoder = nn.Sequential(
+            CausalConv1d(codebook_dim, layer_channels[-1], 7, pad_mode=pad_mode),
+            *[DecoderBlock(co, ci, s, dec_cycle_dilations, squeeze_excite, pad_mode)
+              for (ci, co), s in zip(reversed(pairs), reversed(strides))],
+            CausalConv1d(channels, input_channels, 7, pad_mode=pad_mode))
+        self.register_buffer("zero", torch.tensor(0.0), persistent=False)
+
+    # ---- bookkeeping -----------------------------------------------------------------------------
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def configs(self):
+        return pickle.loads(self._configs)
+
+    @property
+    def seq_len_multiple_of(self):
+        return functools.reduce(lambda a, b: a * b, self.strides)
+
+    @property
+    def downsample_factor(self):
+        return self.seq_len_multiple_of
+
+    def save(self, path):
+        torch.save(dict(model=self.state_dict(), config=self._configs, version="2.4.0"), str(Path(path)))
+
+    def load(self, path, strict=False):
+        """loads encoder / decoder / rq weights; keys of sub-modules outside this build (discriminators,
+        FiLM, mel transforms, local attention) are ignored unless strict=True."""
+        pkg = torch.load(str(Path(path)), map_location="cpu", weights_only=False)
+        sd = pkg["ema_model"] if "ema_model" in pkg else pkg["model"]
+        if "ema_model" in pkg:
+            sd = {k[len("ema_model."):]: v for k, v in sd.items() if k.startswith("ema_model.")}
+        if not strict:
+            mine = self.state_dict()
+            sd = {k: v for k, v in sd.items() if k in mine}
+        self.load_state_dict(sd, strict=strict)
+
+    @classmethod
+    def init_and_load_from(cls, path, strict=False):
+        pkg = torch.load(str(Path(path)), map_location="cpu", weights_only=False)
+        assert "config" in pkg, "model configs were not found in this saved checkpoint"
+        m = cls(**pickle.loads(pkg["config"]))
+        m.load(path, strict=strict)
+        return m.eval()
+
+    # ---- hot path ----------------------------------------------------------------------------------
+    def process_input(self, x, input_sample_hz=None, curtail_from_left=False):
+        lead = x.shape[:-1]
+        x = x.reshape(-1, x.shape[-1])  # the reference packs every leading dim ('* n', soundstream.py:785)
+        if exists(input_sample_hz) and input_sample_hz != self.target_sample_hz:
+            from torchaudio.functional import resample
+            x = resample(x, input_sample_hz, self.target_sample_hz)
+        mult = self.seq_len_multiple_of
+        keep = x.shape[-1] // mult * mult
+        x = x[..., -keep:] if curtail_from_left else x[..., :keep]
+        return x[:, None, :], lead
+
+    def decode_from_codebook_indices(self, quantized_indices):
+        assert quantized_indices.dtype in (torch.long, torch.int32)
+        if quantized_indices.ndim == 3:
+            b, n, gq = quantized_indices.shape
+            quantized_indices = quantized_indices.reshape(b, n, self.rq_groups, -1).permute(2, 0, 1, 3)
+        return self.decode(self.rq.get_output_from_indices(quantized_indices.long()))
+
+    def decode(self, x, quantize=False):
+        if quantize:
+            x, *_ = self.rq(x)
+        return self.decoder(x.transpose(1, 2).contiguous())
+
+    @torch.no_grad()
+    def tokenize(self, audio):
+        self.eval()
+        return self.forward(audio, return_codes_only=True)
+
+    def forward(self, x, target=None, is_denoising=None, return_encoded=False, return_codes_only=False,
+                return_discr_loss=False, return_discr_losses_separately=False, return_loss_breakdown=False,
+                return_recons_only=False, input_sample_hz=None, apply_grad_penalty=False, curtail_from_left=False):
+        if exists(is_denoising) or exists(target):
+            raise NotImplementedError("FiLM denoising / target losses are outside this build")
+        x, lead = self.process_input(x, input_sample_hz=input_sample_hz, curtail_from_left=curtail_from_left)
+        h = self.encoder(x.to(f32)).transpose(1, 2).contiguous()      # b n c
+        quantized, indices, commit_loss = self.rq(h)
+        if return_codes_only:
+            return indices
+        if return_encoded:
+            g, b, n, q = indices.shape
+            return quantized, indices.permute(1, 2, 0, 3).reshape(b, n, g * q), commit_loss
+        recon = self.decoder(quantized.transpose(1, 2).contiguous())
+        if return_recons_only:
+            return recon.reshape(*lead, *recon.shape[-2:]) if len(lead) != 1 else recon
+        raise NotImplementedError("SoundStream training losses (GAN / mel / feature matching) are outside this build")
+
+
+def AudioLMSoundStream(strides=(2, 4, 5, 8), target_sample_hz=16000, rq_num_quantizers=12, **kwargs):
+    return SoundStream(strides=strides, target_sample_hz=target_sample_hz, rq_num_quantizers=rq_num_quantizers, **kwargs)
+
+
+def MusicLMSoundStream(strides=(3, 4, 5, 8), target_sample_hz=24000, rq_num_quantizers=12, **kwargs):
+    return SoundStream(strides=strides, target_sample_hz=target_sample_hz, rq_num_quantizers=rq_num_quantizers, **kwargs)

@@ -110,13 +110,15 @@ def cpu_step_fn(batch):
         (sl, cl), _ = ot.coarse_forward(state, sem, coarse, **hk)
         loss = ot.coarse_wrapper_loss(sl, cl, sem_labels, coarse_labels)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
 
 def run_cpu(steps, warmup, batch=1):
-    torch.set_num_threads(os.cpu_count() or 1)
+    # more than ~32 intra-op threads makes torch's CPU kernels slower at these sizes (measured: 128 threads ->
+    # 113 s/step vs 11 s/step with 8), so the baseline uses min(cores, 32) threads and says so in `cores`
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
     step = cpu_step_fn(batch)
     for _ in range(warmup):
         step()

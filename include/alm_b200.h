@@ -141,6 +141,34 @@ int alm_cast_pad_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int
                       alm_stream_t stream);
 int alm_scale_by_scalar_bf16(void* x, const float* s, int64_t n, alm_stream_t stream);
 
+/* ---- SoundStream codec (fp32) ---------------------------------------------------------------- */
+/*
+ * CausalConv1d (soundstream.py:332-345): left pad = dilation*(K-1) + 1 - stride filled in-kernel
+ * (pad_mode 0 reflect [edge sample excluded], 1 zeros, 2 replicate), then conv with stride/dilation:
+ *   y[b,o,t] = act( bias[o] + sum_c sum_j w[o,c,j] * xpad[b,c,t*stride + j*dilation] ) (+ residual[b,o,t])
+ * act_elu = 1 applies ELU(alpha=1) before the residual add, which fuses a ResidualUnit
+ * (soundstream.py:362-369) into two launches: conv_k7(dil)+ELU, then conv_k1+ELU+skip.
+ * x [B,Cin,T], w [Cout,Cin,K], y [B,Cout,T/stride], all contiguous fp32.
+ */
+int alm_causal_conv1d_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int B,
+                          int Cin, int Cout, int T, int K, int stride, int dilation, int pad_mode, int act_elu,
+                          alm_stream_t stream);
+/* CausalConvTranspose1d (soundstream.py:347-360): kernel 2*stride, output trimmed to n*stride;
+ * x [B,Cin,n], w [Cin,Cout,2*stride], y [B,Cout,n*stride]; polyphase form, 2 taps per input channel. */
+int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                           int n, int stride, alm_stream_t stream);
+/*
+ * Residual VQ, eval path (vector-quantize-pytorch ResidualVQ.forward as called at soundstream.py:840):
+ * for q in 0..Q-1: idx = argmin_c sqrt(max(|r|^2 + |e_c|^2 - 2 r.e_c, 0)) (lowest index on ties);
+ * r -= e_idx; quantized += e_idx.  x [N, D] (row stride ldx), codebooks [Q, C, D], indices [N, Q] int64.
+ * e2_workspace: Q*C floats of scratch.
+ */
+int alm_rvq_encode(const float* x, int64_t ldx, const float* codebooks, float* e2_workspace, float* quantized,
+                   int64_t ldq, int64_t* indices, int64_t ldi, int N, int D, int C, int Q, alm_stream_t stream);
+/* get_output_from_indices (soundstream.py:697): out[n,:] = sum_q codebooks[q][indices[n,q]] (-1 -> skip) */
+int alm_rvq_decode(const int64_t* indices, int64_t ldi, const float* codebooks, float* out, int64_t ldo, int N, int D,
+                   int C, int Q, alm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
