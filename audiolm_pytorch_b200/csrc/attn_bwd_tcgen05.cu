@@ -18,12 +18,13 @@ namespace alm {
 constexpr int AB_T = 128;                     // tile edge (queries or keys)
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;      // 16 KB
-constexpr int AB_THREADS = 192;
+constexpr int AB_THREADS = 320;          // warps 0-7 compute (2 per TMEM lane quadrant), 8 TMA, 9 MMA
+constexpr int AB_TMA_WARP = 8, AB_MMA_WARP = 9;
 constexpr int AB_STAGES = 2;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnBwdParams {
-  const float* lse;      // [b, h, n_q_pad]
+  const float* lse;      // [b, h, n_q_pad]  log2-domain LSE (m + log2 l) as written by the forward
   const float* delta;    // [b, h, n_q_pad]
   const uint8_t* kmask;  // [b, n_k] or null
   __nv_bfloat16* dq;     // [b, n_q, h*64], row stride lddq
@@ -34,6 +35,12 @@ struct AttnBwdParams {
   int causal;
   float scale, scale_log2;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -91,16 +98,16 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int q_per_head = n_qblocks - qb_min;
   const int n_iter = q_per_head > 0 ? q_per_head * p.h : 0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == AB_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1);
     for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == AB_MMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -108,7 +115,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem_ST = tmem_base, tmem_dPT = tmem_base + 128, tmem_dV = tmem_base + 256,
                  tmem_dK = tmem_base + 320;
 
-  if (warp == 4) {
+  if (warp == AB_TMA_WARP) {
     if (lane == 0 && n_iter > 0) {
       mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
       tma_load_3d(sK, &tmK, kv_full, 0, k0, batch);
@@ -127,7 +134,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (++stage == AB_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == AB_MMA_WARP) {
     if (lane == 0 && n_iter > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(AB_T, AB_T, false, false);
       constexpr uint32_t idesc_acc = umma_idesc_bf16_f32(AB_T, AB_D, false, true);
@@ -174,10 +181,12 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   } else {
-    // compute warps: thread == key row
-    const int row = warp * 32 + lane;
+    // compute warps: thread == key row; warps w and w+4 share a TMEM lane quadrant and split the 128 query
+    // columns in two halves (more warps in flight per SM, half the serial work per thread)
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
     const int kj = k0 + row;
-    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const uint32_t lane_sel = uint32_t(quad * 32) << 16;
     bool key_ok = kj < p.n_k;
     if (key_ok && p.kmask != nullptr) key_ok = p.kmask[(size_t)batch * p.n_k + kj] != 0;
     int stage = 0;
@@ -190,8 +199,11 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_after_sync();
       const float* lse_s = sLse + stage * AB_T;
       const float* del_s = sDelta + stage * AB_T;
+      // whole tile below the causal diagonal and inside n_q: only the per-row key flag matters
+      const bool tile_full = (q0 + AB_T <= p.n_q) && (!p.causal || k0 + AB_T - 1 <= q0 + off);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t rs[32], rp[32];
         __syncwarp();
         tmem_ld_32x32b_x32(tmem_ST + lane_sel + c * 32, rs);
@@ -204,9 +216,9 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int e = 0; e < 8; ++e) {
             const int col = c * 32 + g * 8 + e;
             const int qi = q0 + col;
-            const bool ok = key_ok && qi < p.n_q && (!p.causal || kj <= qi + off);
+            const bool ok = key_ok && (tile_full || (qi < p.n_q && (!p.causal || kj <= qi + off)));
             const float s = __uint_as_float(rs[g * 8 + e]);
-            const float pe = ok ? exp2f(s * p.scale_log2 - lse_s[col] * LOG2E) : 0.f;
+            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, -lse_s[col])) : 0.f;
             pv[e] = pe;
             dsv[e] = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - del_s[col]) * p.scale : 0.f;
           }
@@ -229,8 +241,8 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int which = 0; which < 2; ++which) {
       __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) +
                            ((size_t)batch * p.n_k + (kj < p.n_k ? kj : 0)) * (which == 0 ? p.lddv : p.lddk);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = half;
         uint32_t r[32];
         if (n_iter > 0) {
           __syncwarp();
@@ -257,7 +269,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
+  if (warp == AB_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 // ================================================================================================
@@ -295,23 +307,23 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (p.causal) kv_end = min(p.n_k, q0 + AB_T + off);
   const int n_tiles = kv_end > 0 ? (kv_end + AB_T - 1) / AB_T : 0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == AB_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(q_full, 1);
     for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == AB_MMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
 
-  if (warp == 4) {
+  if (warp == AB_TMA_WARP) {
     if (lane == 0 && n_tiles > 0) {
       mbar_arrive_expect_tx(q_full, 2 * AB_TILE);
       tma_load_3d(sQ, &tmQ, q_full, head * AB_D, q0, batch);
@@ -326,7 +338,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (++stage == AB_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == AB_MMA_WARP) {
     if (lane == 0 && n_tiles > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(AB_T, AB_T, false, false);
       constexpr uint32_t idesc_acc = umma_idesc_bf16_f32(AB_T, AB_D, false, true);
@@ -368,11 +380,12 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
   } else {
-    const int row = warp * 32 + lane;
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
     const int qi = q0 + row;
-    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const uint32_t lane_sel = uint32_t(quad * 32) << 16;
     const size_t roff = ((size_t)batch * p.h + head) * p.n_q_pad + qi;
-    const float lse = p.lse[roff] * LOG2E;   // n_q_pad >= n_qblocks*128: always in bounds
+    const float lse = p.lse[roff];          // log2-domain; n_q_pad >= n_qblocks*128: always in bounds
     const float delta = p.delta[roff];
     const int q_limit = p.causal ? qi + off : p.n_k - 1;
     const uint8_t* mrow = p.kmask ? p.kmask + (size_t)batch * p.n_k : nullptr;
@@ -380,8 +393,11 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const int kbase = j * AB_T;
+      const bool tile_full = mrow == nullptr && (q0 + AB_T <= p.n_q) && (kbase + AB_T <= p.n_k) &&
+                             (!p.causal || kbase + AB_T - 1 <= q0 + off);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t rs[32], rp[32];
         __syncwarp();
         tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, rs);
@@ -393,10 +409,13 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int kj = kbase + c * 32 + g * 8 + e;
-            bool ok = qi < p.n_q && kj < p.n_k && kj <= q_limit;
-            if (ok && mrow != nullptr) ok = mrow[kj] != 0;
+            bool ok = tile_full;
+            if (!tile_full) {
+              ok = qi < p.n_q && kj < p.n_k && kj <= q_limit;
+              if (ok && mrow != nullptr) ok = mrow[kj] != 0;
+            }
             const float s = __uint_as_float(rs[g * 8 + e]);
-            const float pe = ok ? exp2f(s * p.scale_log2 - lse) : 0.f;
+            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, -lse)) : 0.f;
             dsv[e] = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - delta) * p.scale : 0.f;
           }
           store_a_chunk(sdS, row, c * 4 + g, dsv);
@@ -411,8 +430,8 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
+      const int c = half;
       uint32_t r[32];
       if (n_tiles > 0) {
         __syncwarp();
@@ -439,7 +458,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
+  if (warp == AB_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace alm

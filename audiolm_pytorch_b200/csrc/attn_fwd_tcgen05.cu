@@ -24,7 +24,7 @@ constexpr int ATT_TMEM_COLS = 256;
 
 struct AttnFwdParams {
   __nv_bfloat16* o;       // [b, n_q, h*64] row stride ldo
-  float* lse;             // [b, h, lse_stride] natural-log LSE of the scaled scores (for backward); may be null
+  float* lse;             // [b, h, lse_stride] log2-domain LSE of the scaled scores (for backward); may be null
   const uint8_t* kmask;   // [b, n_k] 1 = attend, 0 = masked; may be null
   long long ldo, lse_stride;
   int b, h, n_q, n_k;
@@ -288,7 +288,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         *reinterpret_cast<uint4*>(dst + g * 8) = pk;
       }
       if (p.lse != nullptr) {
-        const float lse = l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : INFINITY;
+        const float lse = l_run > 0.f ? (m_run + log2f(l_run)) : INFINITY;  // log2 domain (x ln2 = natural)
         p.lse[((long long)batch * p.h + head) * p.lse_stride + qi] = lse;
       }
     }

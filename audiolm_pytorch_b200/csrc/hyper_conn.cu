@@ -10,6 +10,7 @@
 // token contiguous; M = batch * seq.  One CTA walks tokens with a grid stride; thread t owns the 8
 // contiguous channels [8t, 8t+8) of every stream, so d/8 threads are active (d % 8 == 0, d <= 8192).
 #include "alm_common.cuh"
+#include "hyper_conn_v2.cuh"
 
 namespace alm {
 
@@ -650,6 +651,22 @@ extern "C" int alm_hc_pre_fwd(const void* R_in, const void* Y, const float* beta
   ALM_REQUIRE(streams == HC_S, ALM_ERR_UNSUPPORTED);
   ALM_REQUIRE(d % 8 == 0 && d >= 8 && d <= 8192 && M > 0, ALM_ERR_ARG);
   ALM_REQUIRE((x_expand != nullptr) != (R_in != nullptr), ALM_ERR_ARG);
+  if (d <= 1024) {  // second-generation kernel: 2 warps per token, no CTA-wide barriers
+    hc2::Params p2{gamma_hc, dyn_alpha, dyn_beta, static_alpha, static_beta, alpha_scale, beta_scale, ln_gamma};
+    const int grid = min(ceil_div(M, hc2::TOK), num_sms() * 2);
+    const size_t smem = hc2::fwd_smem(d);
+    if (d <= 512)
+      hc2::pre_fwd_kernel<1><<<grid, hc2::THREADS, smem, stream>>>(
+          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, (__nv_bfloat16*)R_out,
+          (__nv_bfloat16*)bin, (__nv_bfloat16*)xn, beta_out, aux, M, d);
+    else
+      hc2::pre_fwd_kernel<2><<<grid, hc2::THREADS, smem, stream>>>(
+          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, (__nv_bfloat16*)R_out,
+          (__nv_bfloat16*)bin, (__nv_bfloat16*)xn, beta_out, aux, M, d);
+    ALM_CHECK_LAUNCH();
+    ALM_LAUNCHED(1);
+    return ALM_OK;
+  }
   HcParams prm{gamma_hc, dyn_alpha, dyn_beta, static_alpha, static_beta, alpha_scale, beta_scale, ln_gamma};
   const int threads = hc_threads(d);
   HC_DISPATCH(hc_pre_fwd_kernel, hc_grid(M, threads), threads, HC_T * d * sizeof(float), stream,
@@ -672,6 +689,34 @@ extern "C" int alm_hc_pre_bwd(const void* R_in, const void* Y, const float* beta
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(streams == HC_S, ALM_ERR_UNSUPPORTED);
   ALM_REQUIRE(d % 8 == 0 && d >= 8 && d <= 8192 && M > 0, ALM_ERR_ARG);
+  if (d <= 1024) {
+    hc2::Params p2{gamma_hc, dyn_alpha, dyn_beta, static_alpha, static_beta, alpha_scale, beta_scale, ln_gamma};
+    hc2::Grads g2{g_gamma_hc, g_dyn_alpha, g_dyn_beta, g_static_alpha, g_static_beta, g_alpha_scale, g_beta_scale,
+                  g_ln_gamma};
+    const int grid2 = min(ceil_div(M, hc2::TOK), num_sms());
+    const size_t smem = hc2::bwd_smem(d);
+    static bool attr_set = false;
+    if (!attr_set) {
+      ALM_CUDA_OK(cudaFuncSetAttribute(hc2::pre_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)hc2::bwd_smem(512)));
+      ALM_CUDA_OK(cudaFuncSetAttribute(hc2::pre_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)hc2::bwd_smem(1024)));
+      attr_set = true;
+    }
+    if (d <= 512)
+      hc2::pre_bwd_kernel<1><<<grid2, hc2::THREADS, smem, stream>>>(
+          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, aux,
+          (const __nv_bfloat16*)dR_out, (const __nv_bfloat16*)dxn, (const __nv_bfloat16*)dbin_extra, dbeta,
+          (__nv_bfloat16*)dR_in, (__nv_bfloat16*)dY, dbeta_prev, dx_expand, dx_scale, g2, M, d);
+    else
+      hc2::pre_bwd_kernel<2><<<grid2, hc2::THREADS, smem, stream>>>(
+          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, aux,
+          (const __nv_bfloat16*)dR_out, (const __nv_bfloat16*)dxn, (const __nv_bfloat16*)dbin_extra, dbeta,
+          (__nv_bfloat16*)dR_in, (__nv_bfloat16*)dY, dbeta_prev, dx_expand, dx_scale, g2, M, d);
+    ALM_CHECK_LAUNCH();
+    ALM_LAUNCHED(1);
+    return ALM_OK;
+  }
   HcParams prm{gamma_hc, dyn_alpha, dyn_beta, static_alpha, static_beta, alpha_scale, beta_scale, ln_gamma};
   HcGrads gr{g_gamma_hc, g_dyn_alpha, g_dyn_beta, g_static_alpha, g_static_beta, g_alpha_scale, g_beta_scale,
              g_ln_gamma};

@@ -1,0 +1,516 @@
+// Hyper-Connections kernels, second generation: 2 warps per token, 4 tokens per CTA, no CTA-wide barrier.
+// (The first generation in hyper_conn.cu used one CTA per token with 5-6 __syncthreads per token and ran
+// 8-14x off the HBM roofline: profiles/r01_launches_bench_step_v1.csv.)
+//
+//  - a token's 64 threads each own NCH chunks of 8 channels (16-B vector loads, fully coalesced);
+//  - reductions: warp shuffle + one 64-thread named barrier (bar.sync id, 64) through a tiny smem mailbox;
+//  - per-channel parameters live in shared memory (fp32); parameter gradients are accumulated in shared
+//    memory with red.shared and flushed once per CTA with global atomics.
+#pragma once
+#include "alm_common.cuh"
+
+namespace alm {
+namespace hc2 {
+
+constexpr int S = 4, T = 5;
+constexpr int TOK = 4;            // token slots per CTA
+constexpr int THREADS = 64 * TOK;
+constexpr int AUX = S * T + S + S + 2;
+
+__device__ __forceinline__ void bar64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// sum N values over the 64 threads of a token slot; all of them get the result.
+template <int N>
+__device__ __forceinline__ void slot_sum(float (&v)[N], float* mail /*[2][2][N_MAX]*/, int& which, int w2, int lane,
+                                         int bar_id) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  float* b = mail + which * (2 * 24);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) b[w2 * 24 + i] = v[i];
+  }
+  bar64(bar_id);
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = b[i] + b[24 + i];
+  which ^= 1;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pk(f[0], f[1]), pk(f[2], f[3]), pk(f[4], f[5]), pk(f[6], f[7]));
+}
+
+struct Params {
+  const float* gamma_hc; const float* dyn_alpha; const float* dyn_beta; const float* static_alpha;
+  const float* static_beta; const float* alpha_scale; const float* beta_scale; const float* ln_gamma;
+};
+struct Grads {
+  float* gamma_hc; float* dyn_alpha; float* dyn_beta; float* static_alpha; float* static_beta;
+  float* alpha_scale; float* beta_scale; float* ln_gamma;
+};
+
+// smem: [0,d) g1 = (gamma+1)*sqrt(d); [d,2d) dyn_beta; [2d,3d) ln_gamma; [3d, 8d) dyn_alpha transposed [T][d]
+__device__ __forceinline__ void stage_params(float* sm, const Params& p, int d) {
+  const float sqrt_d = sqrtf((float)d);
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    sm[i] = (p.gamma_hc[i] + 1.f) * sqrt_d;
+    sm[d + i] = p.dyn_beta[i];
+    sm[2 * d + i] = p.ln_gamma[i];
+#pragma unroll
+    for (int t = 0; t < T; ++t) sm[(3 + t) * d + i] = p.dyn_alpha[(size_t)i * T + t];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(THREADS, 2)
+pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __restrict__ Y,
+               const float* __restrict__ beta_prev, const float* __restrict__ x_expand, Params prm,
+               __nv_bfloat16* __restrict__ R_out, __nv_bfloat16* __restrict__ bin, __nv_bfloat16* __restrict__ xn,
+               float* __restrict__ beta_out, float* __restrict__ aux, int M, int d) {
+  extern __shared__ float sm[];
+  float* mailbox = sm + 8 * d;  // [TOK][2][2][24]
+  stage_params(sm, prm, d);
+  __syncthreads();
+  const float* sG1 = sm;
+  const float* sBf = sm + d;
+  const float* sLn = sm + 2 * d;
+  const float* sA = sm + 3 * d;
+  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
+  float* mail = mailbox + slot * (2 * 2 * 24);
+  int which = 0;
+  const int bar_id = 1 + slot;
+  const float a_scale = *prm.alpha_scale, b_scale = *prm.beta_scale;
+  float Astat[S][T], Bstat[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    Bstat[s] = prm.static_beta[s];
+#pragma unroll
+    for (int t = 0; t < T; ++t) Astat[s][t] = prm.static_alpha[s * T + t];
+  }
+  int ch[NCH];
+  bool act[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) { ch[k] = (lt + 64 * k) * 8; act[k] = ch[k] < d; }
+
+  for (int m = blockIdx.x * TOK + slot; m < M; m += gridDim.x * TOK) {
+    float R[S][NCH][8];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      if (act[k]) {
+        if (x_expand != nullptr) {
+          const float4 a = *reinterpret_cast<const float4*>(x_expand + (size_t)m * d + ch[k]);
+          const float4 b = *reinterpret_cast<const float4*>(x_expand + (size_t)m * d + ch[k] + 4);
+          const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) R[s][k][e] = xv[e];
+        } else {
+          float yv[8];
+          unpack8(*reinterpret_cast<const uint4*>(Y + (size_t)m * d + ch[k]), yv);
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float rv[8];
+            unpack8(*reinterpret_cast<const uint4*>(R_in + ((size_t)m * S + s) * d + ch[k]), rv);
+            const float bp = beta_prev[(size_t)m * S + s];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) R[s][k][e] = fmaf(bp, yv[e], rv[e]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) R[s][k][e] = 0.f;
+      }
+    }
+    float ssq[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a = fmaf(R[s][k][e], R[s][k][e], a);
+      ssq[s] = a;
+    }
+    slot_sum<S>(ssq, mail, which, w2, lane, bar_id);
+    float inv[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) inv[s] = 1.f / fmaxf(sqrtf(ssq[s]), 1e-12f);
+    float w[S * T + S];
+#pragma unroll
+    for (int i = 0; i < S * T + S; ++i) w[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      if (act[k]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = ch[k] + e;
+          const float g1 = sG1[c], bf = sBf[c];
+          float av[T];
+#pragma unroll
+          for (int t = 0; t < T; ++t) av[t] = sA[t * d + c];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const float nv = R[s][k][e] * inv[s] * g1;
+#pragma unroll
+            for (int t = 0; t < T; ++t) w[s * T + t] = fmaf(nv, av[t], w[s * T + t]);
+            w[S * T + s] = fmaf(nv, bf, w[S * T + s]);
+          }
+        }
+      }
+    }
+    slot_sum<S * T + S>(w, mail, which, w2, lane, bar_id);
+    float alpha[S][T], beta[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        w[s * T + t] = tanhf(w[s * T + t]);
+        alpha[s][t] = fmaf(w[s * T + t], a_scale, Astat[s][t]);
+      }
+      w[S * T + s] = tanhf(w[S * T + s]);
+      beta[s] = fmaf(w[S * T + s], b_scale, Bstat[s]);
+    }
+    // mixed residual streams out; branch input kept for the LayerNorm
+    float bi[NCH][8];
+    float st[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) a = fmaf(alpha[s][0], R[s][k][e], a);
+        bi[k][e] = a;
+        st[0] += a;
+      }
+      if (act[k]) {
+#pragma unroll
+        for (int t = 1; t < T; ++t) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) a = fmaf(alpha[s][t], R[s][k][e], a);
+            o[e] = a;
+          }
+          *reinterpret_cast<uint4*>(R_out + ((size_t)m * S + (t - 1)) * d + ch[k]) = pack8(o);
+        }
+        *reinterpret_cast<uint4*>(bin + (size_t)m * d + ch[k]) = pack8(bi[k]);
+      }
+    }
+    slot_sum<1>(st, mail, which, w2, lane, bar_id);
+    const float mean = st[0] / d;
+    float sv[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+      if (act[k]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sv[0] = fmaf(bi[k][e] - mean, bi[k][e] - mean, sv[0]);
+      }
+    slot_sum<1>(sv, mail, which, w2, lane, bar_id);
+    const float rstd = rsqrtf(sv[0] / d + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+      if (act[k]) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (bi[k][e] - mean) * rstd * sLn[ch[k] + e];
+        *reinterpret_cast<uint4*>(xn + (size_t)m * d + ch[k]) = pack8(o);
+      }
+    if (lt == 0) {
+      float* a = aux + (size_t)m * AUX;
+#pragma unroll
+      for (int i = 0; i < S * T + S; ++i) a[i] = w[i];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        a[S * T + S + s] = inv[s];
+        beta_out[(size_t)m * S + s] = beta[s];
+      }
+      a[AUX - 2] = mean;
+      a[AUX - 1] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// smem for the backward adds gradient accumulators: [8d, 16d): gG, gBf, gLn, gA[T]  (same order as params)
+template <int NCH>
+__global__ void __launch_bounds__(THREADS, 1)
+pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __restrict__ Y,
+               const float* __restrict__ beta_prev, const float* __restrict__ x_expand, Params prm,
+               const float* __restrict__ aux, const __nv_bfloat16* __restrict__ dR_out,
+               const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16* __restrict__ dbin_extra,
+               const float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dR_in, __nv_bfloat16* __restrict__ dY,
+               float* __restrict__ dbeta_prev, float* __restrict__ dx_expand, float dx_scale, Grads gr, int M,
+               int d) {
+  extern __shared__ float sm[];
+  float* sGrad = sm + 8 * d;         // [8][d]
+  float* mailbox = sm + 16 * d;      // [TOK][2][2][24]
+  stage_params(sm, prm, d);
+  for (int i = threadIdx.x; i < 8 * d; i += blockDim.x) sGrad[i] = 0.f;
+  __syncthreads();
+  const float* sG1 = sm;
+  const float* sBf = sm + d;
+  const float* sLn = sm + 2 * d;
+  const float* sA = sm + 3 * d;
+  float* gG = sGrad;
+  float* gBf = sGrad + d;
+  float* gLn = sGrad + 2 * d;
+  float* gA = sGrad + 3 * d;
+  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
+  float* mail = mailbox + slot * (2 * 2 * 24);
+  int which = 0;
+  const int bar_id = 1 + slot;
+  const float sqrt_d = sqrtf((float)d);
+  const float a_scale = *prm.alpha_scale, b_scale = *prm.beta_scale;
+  float Astat[S][T];
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int t = 0; t < T; ++t) Astat[s][t] = prm.static_alpha[s * T + t];
+  float acc_small[S * T + S + 2];
+#pragma unroll
+  for (int i = 0; i < S * T + S + 2; ++i) acc_small[i] = 0.f;
+  int ch[NCH];
+  bool act[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) { ch[k] = (lt + 64 * k) * 8; act[k] = ch[k] < d; }
+
+  for (int m = blockIdx.x * TOK + slot; m < M; m += gridDim.x * TOK) {
+    const float* a = aux + (size_t)m * AUX;
+    float ta[S][T], tb[S], inv[S], alpha[S][T], bp[S], dbe[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        ta[s][t] = a[s * T + t];
+        alpha[s][t] = fmaf(ta[s][t], a_scale, Astat[s][t]);
+      }
+      tb[s] = a[S * T + s];
+      inv[s] = a[S * T + S + s];
+      dbe[s] = dbeta[(size_t)m * S + s];
+      bp[s] = (x_expand == nullptr) ? beta_prev[(size_t)m * S + s] : 0.f;
+    }
+    const float mean = a[AUX - 2], rstd = a[AUX - 1];
+
+    float R[S][NCH][8], yv[NCH][8], dmix[T][NCH][8];
+    float lnred[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[k][e] = 0.f;
+      if (act[k]) {
+        if (x_expand != nullptr) {
+          const float4 xa = *reinterpret_cast<const float4*>(x_expand + (size_t)m * d + ch[k]);
+          const float4 xb = *reinterpret_cast<const float4*>(x_expand + (size_t)m * d + ch[k] + 4);
+          const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) R[s][k][e] = xv[e];
+        } else {
+          unpack8(*reinterpret_cast<const uint4*>(Y + (size_t)m * d + ch[k]), yv[k]);
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float rv[8];
+            unpack8(*reinterpret_cast<const uint4*>(R_in + ((size_t)m * S + s) * d + ch[k]), rv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) R[s][k][e] = fmaf(bp[s], yv[k][e], rv[e]);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          unpack8(*reinterpret_cast<const uint4*>(dR_out + ((size_t)m * S + s) * d + ch[k]), dmix[s + 1][k]);
+        // LayerNorm backward, part 1 (dmix[0] temporarily holds gl = dxn * ln_gamma)
+        float dx8[8];
+        unpack8(*reinterpret_cast<const uint4*>(dxn + (size_t)m * d + ch[k]), dx8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float b = 0.f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) b = fmaf(alpha[s][0], R[s][k][e], b);
+          const float xhat = (b - mean) * rstd;
+          const float gl = dx8[e] * sLn[ch[k] + e];
+          atomicAdd(&gLn[ch[k] + e], dx8[e] * xhat);
+          lnred[0] += gl;
+          lnred[1] = fmaf(gl, xhat, lnred[1]);
+          dmix[0][k][e] = gl;
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { R[s][k][e] = 0.f; dmix[s + 1][k][e] = 0.f; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dmix[0][k][e] = 0.f;
+      }
+    }
+    slot_sum<2>(lnred, mail, which, w2, lane, bar_id);
+    const float m1 = lnred[0] / d, m2 = lnred[1] / d;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+      if (act[k]) {
+        float ex[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ex[e] = 0.f;
+        if (dbin_extra != nullptr) unpack8(*reinterpret_cast<const uint4*>(dbin_extra + (size_t)m * d + ch[k]), ex);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float b = 0.f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) b = fmaf(alpha[s][0], R[s][k][e], b);
+          const float xhat = (b - mean) * rstd;
+          dmix[0][k][e] = rstd * (dmix[0][k][e] - m1 - xhat * m2) + ex[e];
+        }
+      }
+    // d alpha
+    float dal[S * T];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(dmix[t][k][e], R[s][k][e], acc);
+        dal[s * T + t] = acc;
+      }
+    slot_sum<S * T>(dal, mail, which, w2, lane, bar_id);
+    float dwa[S][T], dwb[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float g = dal[s * T + t];
+        dwa[s][t] = g * a_scale * (1.f - ta[s][t] * ta[s][t]);
+        acc_small[s * T + t] += g;
+        acc_small[S * T + S] = fmaf(g, ta[s][t], acc_small[S * T + S]);
+      }
+      dwb[s] = dbe[s] * b_scale * (1.f - tb[s] * tb[s]);
+      acc_small[S * T + s] += dbe[s];
+      acc_small[S * T + S + 1] = fmaf(dbe[s], tb[s], acc_small[S * T + S + 1]);
+    }
+    // dR (written in place over dmix[0..3]) + parameter-gradient contributions
+    float udot[S] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      if (act[k]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = ch[k] + e;
+          const float g1 = sG1[c], bf = sBf[c];
+          float av[T], dm[T];
+#pragma unroll
+          for (int t = 0; t < T; ++t) { av[t] = sA[t * d + c]; dm[t] = dmix[t][k][e]; }
+          float pG = 0.f, pBf = 0.f, pA[T] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc = fmaf(alpha[s][t], dm[t], acc);
+            float dn = dwb[s] * bf;
+#pragma unroll
+            for (int t = 0; t < T; ++t) dn = fmaf(dwa[s][t], av[t], dn);
+            const float rn = R[s][k][e] * inv[s];
+            const float nv = rn * g1;
+            pG = fmaf(dn * rn, sqrt_d, pG);
+            pBf = fmaf(nv, dwb[s], pBf);
+#pragma unroll
+            for (int t = 0; t < T; ++t) pA[t] = fmaf(nv, dwa[s][t], pA[t]);
+            const float u = dn * g1;
+            udot[s] = fmaf(u, R[s][k][e], udot[s]);
+            dmix[s][k][e] = fmaf(u, inv[s], acc);  // dR[s] (dm[] was read above)
+          }
+          atomicAdd(&gG[c], pG);
+          atomicAdd(&gBf[c], pBf);
+#pragma unroll
+          for (int t = 0; t < T; ++t) atomicAdd(&gA[t * d + c], pA[t]);
+        }
+      }
+    }
+    slot_sum<S>(udot, mail, which, w2, lane, bar_id);
+    float dbp[S] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float kk = udot[s] * inv[s] * inv[s] * inv[s];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dmix[s][k][e] = fmaf(-R[s][k][e], kk, dmix[s][k][e]);
+          dbp[s] = fmaf(dmix[s][k][e], yv[k][e], dbp[s]);
+        }
+    }
+    if (x_expand != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+        if (act[k]) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = (dmix[0][k][e] + dmix[1][k][e] + dmix[2][k][e] + dmix[3][k][e]) * dx_scale;
+          float* dst = dx_expand + (size_t)m * d + ch[k];
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    } else {
+      slot_sum<S>(dbp, mail, which, w2, lane, bar_id);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+        if (act[k]) {
+          float dy[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc = fmaf(bp[s], dmix[s][k][e], acc);
+            dy[e] = acc;
+          }
+          *reinterpret_cast<uint4*>(dY + (size_t)m * d + ch[k]) = pack8(dy);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            *reinterpret_cast<uint4*>(dR_in + ((size_t)m * S + s) * d + ch[k]) = pack8(dmix[s][k]);
+        }
+      if (lt == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) dbeta_prev[(size_t)m * S + s] = dbp[s];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(gr.gamma_hc + i, gG[i]);
+    atomicAdd(gr.dyn_beta + i, gBf[i]);
+    atomicAdd(gr.ln_gamma + i, gLn[i]);
+#pragma unroll
+    for (int t = 0; t < T; ++t) atomicAdd(gr.dyn_alpha + (size_t)i * T + t, gA[t * d + i]);
+  }
+  if (lt == 0) {  // one thread per token slot holds that slot's scalar-parameter partial sums
+#pragma unroll
+    for (int i = 0; i < S * T; ++i) atomicAdd(gr.static_alpha + i, acc_small[i]);
+#pragma unroll
+    for (int s = 0; s < S; ++s) atomicAdd(gr.static_beta + s, acc_small[S * T + s]);
+    atomicAdd(gr.alpha_scale, acc_small[S * T + S]);
+    atomicAdd(gr.beta_scale, acc_small[S * T + S + 1]);
+  }
+}
+
+inline size_t fwd_smem(int d) { return (size_t)(8 * d + TOK * 2 * 2 * 24) * sizeof(float); }
+inline size_t bwd_smem(int d) { return (size_t)(16 * d + TOK * 2 * 2 * 24) * sizeof(float); }
+
+}  // namespace hc2
+}  // namespace alm

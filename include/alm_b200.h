@@ -60,7 +60,7 @@ int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const v
  * o[b,i,h*64:(h+1)*64] = softmax_j( q[b,i,h,:]·k[b,j,:] * scale, masked ) · v[b,j,:]
  *   one shared k/v head of width 64 (MQA); key_mask[b,j] (uint8, 1 = attend) optional;
  *   causal: query i sees keys j <= i + (n_k - n_q) (right-aligned, as needed by the KV cache).
- *   lse[b,h,i] (optional, row stride lse_stride >= n_q) = log-sum-exp of the scaled, masked scores (natural log) for the backward.
+ *   lse[b,h,i] (optional, row stride lse_stride >= n_q) = log2-domain log-sum-exp (log2 sum_j 2^(s_ij*scale*log2e)) of the masked scores for the backward.
  * Replaces Attend.forward / flash_attn (attend.py:69-146) as called by Attention.forward
  * (audiolm_pytorch.py:390).  Fully masked rows produce zeros (the reference's flash path yields NaN).
  * q rows stride ldq (q may be a column slice of a fused qkv buffer); k/v rows stride ldk/ldv, batch

@@ -56,4 +56,4 @@ def test_attn_fwd(b, h, n_q, n_k, masked, causal):
     err = (o.float() - ref).abs().max().item()
     assert err <= 2e-2 * max(1.0, ref.abs().max().item()), f"attention out err {err}"
     lse_ref = torch.logsumexp(sim, dim=-1)
-    assert (lse[..., :n_q] - lse_ref).abs().max().item() <= 2e-2
+    assert (lse[..., :n_q] * 0.6931471805599453 - lse_ref).abs().max().item() <= 2e-2  # kernel stores log2-domain LSE
