@@ -15,6 +15,7 @@ f32 = torch.float32
 
 # ---- optional in-stream kernel timing (bench.py roofline): CUDA events bracket each tagged launch -----
 _PROFILE = None
+PROFILE_SHAPES = False  # per-shape GEMM classes (tools/profile_step.py)
 
 
 def profile_start():
@@ -94,7 +95,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, alpha=1.0, b
     assert o3.dtype in (bf16, f32)
     if bias is not None:
         assert bias.dtype == f32 and bias.numel() == N and bias.is_contiguous()
-    with _timed("gemm_bf16_tcgen05", 2.0 * M * N * K * nb):
+    cls = "gemm_bf16_tcgen05"
+    if _PROFILE is not None and PROFILE_SHAPES:
+        cls += f" M{M} N{N} K{K} b{nb} {'mn' if a_mn else 'k'}{'mn' if b_mn else 'k'} s{split_k}"
+    with _timed(cls, 2.0 * M * N * K * nb):
         _lib.call(
             "alm_gemm_bf16",
             a3, int(a_mn), a3.stride(1), a3.stride(0) if nb > 1 else 0,

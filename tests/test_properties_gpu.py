@@ -1,0 +1,133 @@
+"""B200, BASELINE.json full sizes: size-independent properties of the CUDA path (no oracle needed)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+C3 = dict(num_semantic_tokens=500, codebook_size=1024, num_coarse_quantizers=3, dim=1024, depth=6, heads=8,
+          flash_attn=True)
+
+
+@pytest.fixture(scope="module")
+def coarse_model():
+    from audiolm_pytorch_b200.audiolm import CoarseTransformer
+
+    torch.manual_seed(11)
+    m = CoarseTransformer(**C3)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "dynamic_alpha_fn" in n or "dynamic_beta_fn" in n:
+                p.normal_(0, 0.02)
+            if "logit_weights" in n:
+                p.mul_(0.05)
+    return m.to(DEV).eval()
+
+
+def test_c3_causality_and_batch_independence(coarse_model):
+    """seq 2048: logits at positions < t do not change when tokens >= t change; rows of a batch are independent."""
+    torch.manual_seed(0)
+    sem = torch.randint(0, 500, (2, 372), device=DEV)
+    coarse = torch.randint(0, 1024, (2, 1674), device=DEV)
+    with torch.no_grad():
+        sl, cl = coarse_model(semantic_token_ids=sem, coarse_token_ids=coarse)
+        c2 = coarse.clone()
+        c2[:, 1000:] = torch.randint(0, 1024, (2, 674), device=DEV)
+        sl2, cl2 = coarse_model(semantic_token_ids=sem, coarse_token_ids=c2)
+        sl3, cl3 = coarse_model(semantic_token_ids=sem[1:], coarse_token_ids=coarse[1:])
+    assert cl.shape == (2, 1675, 1025) and sl.shape == (2, 372, 501)
+    assert torch.equal(sl, sl2)                      # semantic positions precede every changed token
+    assert torch.equal(cl[:, :1001], cl2[:, :1001])  # coarse logit p depends on coarse ids < p only
+    assert not torch.equal(cl[:, 1001:], cl2[:, 1001:])
+    assert torch.equal(cl[1:], cl3) and torch.equal(sl[1:], sl3)
+    assert torch.isfinite(cl).all()
+
+
+def test_c3_kv_cache_equals_full_forward(coarse_model):
+    """incremental decode with kv_cache/embed_cache reproduces the full forward at seq 2048 (reference
+    self-consistency property)."""
+    torch.manual_seed(1)
+    sem = torch.randint(0, 500, (1, 372), device=DEV)
+    coarse = torch.randint(0, 1024, (1, 1674), device=DEV)
+    with torch.no_grad():
+        (_, full), _ = coarse_model(semantic_token_ids=sem, coarse_token_ids=coarse, return_cache=True,
+                                    return_only_coarse_logits=True)
+        (_, _), (kv, emb) = coarse_model(semantic_token_ids=sem, coarse_token_ids=coarse[:, :1500], return_cache=True,
+                                         return_only_coarse_logits=True)
+        (_, inc), _ = coarse_model(semantic_token_ids=sem, coarse_token_ids=coarse, return_cache=True, kv_cache=kv,
+                                   embed_cache=emb, return_only_coarse_logits=True)
+    err = (inc - full).abs().max().item() / full.abs().max().item()
+    assert err < 2e-2, err
+
+
+def test_c3_gradient_linearity(coarse_model):
+    """d(2*loss) == 2*d(loss) through the whole hand-written backward (bit-level up to bf16 rounding of dout)."""
+    from audiolm_pytorch_b200.heads import cross_entropy
+
+    coarse_model.train()
+    torch.manual_seed(2)
+    sem = torch.randint(0, 500, (2, 372), device=DEV)
+    coarse = torch.randint(0, 1024, (2, 1674), device=DEV)
+    labels = torch.cat((coarse, torch.full((2, 1), 1024, device=DEV)), 1)
+    grads = []
+    for scale in (1.0, 2.0):
+        for p in coarse_model.parameters():
+            p.grad = None
+        _, cl = coarse_model(semantic_token_ids=sem, coarse_token_ids=coarse)
+        (cross_entropy(cl, labels) * scale).backward()
+        grads.append(coarse_model.transformer.layers[3][2].branch.get_submodule("1").weight.grad.clone())
+    coarse_model.eval()
+    rel = (grads[1] - 2 * grads[0]).abs().max().item() / grads[1].abs().max().item()
+    assert rel < 2e-2, rel
+
+
+def test_gemm_linearity_full_ffn_shape():
+    from audiolm_pytorch_b200 import ops
+
+    torch.manual_seed(3)
+    a1 = torch.randn(4096, 1024, device=DEV).to(torch.bfloat16)
+    a2 = torch.randn(4096, 1024, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(5472, 1024, device=DEV) * 0.03).to(torch.bfloat16)
+    y1 = ops.gemm(a1, w, out_dtype=torch.float32)
+    y2 = ops.gemm(a2, w, out_dtype=torch.float32)
+    y12 = ops.gemm((a1.float() + a2.float()).to(torch.bfloat16), w, out_dtype=torch.float32)
+    # (a1 + a2) is re-rounded to bf16, hence the tolerance
+    assert (y12 - (y1 + y2)).abs().max().item() < 2e-2 * y12.abs().max().item()
+    # transposed-operand forms agree with the plain form: (a w^T)^T == w a^T
+    yt = ops.gemm(w, a1, out_dtype=torch.float32)
+    assert torch.equal(yt.t().contiguous(), y1) or (yt.t() - y1).abs().max().item() < 1e-3 * y1.abs().max().item()
+
+
+def test_c1_codec_properties():
+    """2 s @ 24 kHz clips: 150 frames, indices in range, residual energy falls with every RVQ stage, decode of the
+    emitted indices reproduces `quantized`, encoder causality past the reflect halo."""
+    from audiolm_pytorch_b200 import ops
+    from audiolm_pytorch_b200.soundstream import SoundStream
+
+    torch.manual_seed(4)
+    ss = SoundStream(codebook_size=1024, rq_num_quantizers=8, target_sample_hz=24000, use_local_attn=False)
+    for layer in ss.rq.rvqs[0].layers:
+        layer._codebook.embed.normal_(0, 0.3)
+        layer._codebook.initted.fill_(True)
+    ss = ss.to(DEV).eval()
+    wave = torch.randn(4, 48000, device=DEV)
+    with torch.no_grad():
+        quant, idx, _ = ss(wave, return_encoded=True)
+        enc = ss.encoder(wave[:, None]).transpose(1, 2).contiguous()
+        cb = ss.rq.rvqs[0].codebooks()
+        assert idx.shape == (4, 150, 8) and idx.min() >= 0 and idx.max() < 1024
+        dec = ops.rvq_decode(idx.reshape(-1, 8), cb).view(4, 150, 512)
+        assert (dec - quant).abs().max().item() < 1e-4
+        prev = enc.reshape(-1, 512).pow(2).sum(-1)
+        for q in range(1, 9):
+            part = ops.rvq_decode(idx.reshape(-1, 8)[:, :q].contiguous(), cb[:q])
+            cur = (enc.reshape(-1, 512) - part).pow(2).sum(-1)
+            assert (cur <= prev + 1e-3).all()   # nearest-code subtraction never increases the residual norm
+            prev = cur
+        w2 = wave.clone()
+        w2[:, 24000:] += 1.0
+        enc2 = ss.encoder(w2[:, None]).transpose(1, 2)
+        assert torch.equal(enc2[:, :74], enc[:, :74])  # frames fully before sample 24000 (75 * 320) are unchanged
+        recon = ss(wave, return_recons_only=True)
+        assert recon.shape == (4, 1, 48000)
+        assert torch.allclose(ss.decode_from_codebook_indices(idx), recon, atol=1e-5)
