@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .heads import (HeadCache, cross_entropy, generate_mask_with_prob, gumbel_sample, mask_out_after_eos_id, top_k)
+from . import ops
 from .transformer import Transformer, default, exists
 
 __version__ = "2.4.0"  # checkpoint 'version' field of the reference this surface mirrors
@@ -279,7 +280,12 @@ def _eval_no_grad(fn):
 
 
 def _sample_next(last_logits, filter_thres, temperature):
-    return gumbel_sample(top_k(last_logits, thres=filter_thres), temperature=temperature, dim=-1)[:, None]
+    """top_k(thres) + gumbel_sample (audiolm_pytorch.py:1498-1499): the uniform noise comes from torch (same
+    draw as `zeros_like(t).uniform_(0, 1)`), the filter + Gumbel-max runs in one alm_topk_gumbel_sample launch."""
+    last_logits = last_logits.float().contiguous()
+    k = max(int((1 - filter_thres) * last_logits.shape[-1]), 1)
+    noise = torch.zeros_like(last_logits).uniform_(0, 1)
+    return ops.topk_gumbel_sample(last_logits, noise, k=k, temperature=temperature)[:, None]
 
 
 class SemanticTransformerWrapper(nn.Module):

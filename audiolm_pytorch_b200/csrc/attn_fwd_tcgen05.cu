@@ -17,9 +17,10 @@ constexpr int ATT_BM = 128;     // queries per CTA
 constexpr int ATT_BN = 128;     // keys per tile
 constexpr int ATT_D = 64;       // head width (dim_head)
 constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;   // warps 0-7 softmax (2 per TMEM lane quadrant), warp 8 TMA, warp 9 MMA
+constexpr int ATT_TMA_WARP = 8, ATT_MMA_WARP = 9;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 SW128 tile
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 + 2 * ATT_KV_STAGES) + 256;  // 2 CTAs/SM: no align slack
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 + 2 * ATT_KV_STAGES) + 256;  // 2 CTAs/SM: must stay <= 113 KB
 constexpr int ATT_TMEM_COLS = 256;
 
 struct AttnFwdParams {
@@ -66,7 +67,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (p.causal) kv_end = min(p.n_k, q0 + ATT_BM + off);
   const int n_tiles = kv_end > 0 ? (kv_end + ATT_BN - 1) / ATT_BN : 0;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == ATT_TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -76,11 +77,11 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);  // one arrive per softmax warp
+    mbar_init(p_full, 8);  // one arrive per softmax warp
     mbar_init(pv_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  if (warp == ATT_MMA_WARP) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -88,7 +89,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_PV = tmem_base + ATT_BN;
 
-  if (warp == 4) {
+  if (warp == ATT_TMA_WARP) {
     if (lane == 0 && n_tiles > 0) {
       // ---------------- TMA producer ----------------
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
@@ -103,7 +104,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == ATT_MMA_WARP) {
     if (lane == 0 && n_tiles > 0) {
       // ---------------- UMMA issuer ----------------
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(ATT_BM, ATT_BN, false, false);   // Q K^T
@@ -143,22 +144,36 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else {
-    // ---------------- softmax warps: thread == query row ----------------
-    const int row = warp * 32 + lane;
+    // ---------------- softmax warps ----------------
+    // thread == query row; warps w and w+4 share a TMEM lane quadrant: `half` 0/1 owns key columns
+    // [0,64) / [64,128) of every S tile (== P k-tile 0 / 1) and output channels [0,32) / [32,64).
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
     const int qi = q0 + row;
-    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const uint32_t lane_sel = uint32_t(quad * 32) << 16;
+    const int pair_bar = 1 + quad;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    float o_acc[ATT_D];
+    float o_acc[32];
 #pragma unroll
-    for (int d = 0; d < ATT_D; ++d) o_acc[d] = 0.f;
+    for (int d = 0; d < 32; ++d) o_acc[d] = 0.f;
     const int q_limit = p.causal ? qi + off : p.n_k - 1;  // last key index this query may see
     const uint8_t* mrow = p.kmask ? p.kmask + (long long)batch * p.n_k : nullptr;
+    uint8_t* ptile = sP + half * ATT_TILE_BYTES;
+
+    auto add_pv = [&](float a) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld_32x32b_x32(tmem_PV + lane_sel + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o_acc[e] = fmaf(o_acc[e], a, __uint_as_float(r[e]));
+    };
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const int kbase = j * ATT_BN;
-      // key validity bits for this tile (uniform across the CTA except for the causal limit)
+      // key validity bits of the whole 128-key tile (the row max needs all of it)
       uint32_t valid[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
       if (mrow != nullptr) {
 #pragma unroll
@@ -191,8 +206,8 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t range = hi >= 31 ? 0xFFFFFFFFu : (hi < 0 ? 0u : ((2u << hi) - 1u));
         valid[w] &= range;
       }
-
-      // pass 1: row max
+      // pass 1: row max over all 128 keys (both warps of a quadrant compute it redundantly: TMEM reads are
+      // cheap, and it avoids a cross-warp exchange); pass 2 below only touches this warp's 64 columns
       float m_tile = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -207,39 +222,28 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = exp2f(m_run - m_use);  // m_run == -inf -> 0
-      float l_tile = 0.f;
-
-      // previous tile's P V must have been consumed before sP is overwritten
+      // previous tile's P V must be consumed before sP is overwritten
       if (j > 0) {
         mbar_wait(pv_full, (j - 1) & 1);
         tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(tmem_PV + lane_sel + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = o_acc[c * 32 + e] * alpha_prev + __uint_as_float(r[e]);
-        }
+        add_pv(alpha_prev);
       }
-
-      // pass 2: p = exp2(s*scale - m), write bf16 P into the SW128 K-major A-operand layout
+      // pass 2: p = exp2(s*scale - m) -> bf16 P in the SW128 K-major A-operand layout
+      float l_tile = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t r[32];
         __syncwarp();
-        tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, r);
+        tmem_ld_32x32b_x32(tmem_S + lane_sel + half * 64 + cc * 32, r);
         tmem_ld_wait();
         float pe[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const float s = __uint_as_float(r[e]);
-          const float pv = ((valid[c] >> e) & 1u) ? exp2f(s * p.scale_log2 - m_use) : 0.f;
+          const float pv =
+              ((valid[half * 2 + cc] >> e) & 1u) ? exp2f(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_use)) : 0.f;
           pe[e] = pv;
           l_tile += pv;
         }
-        uint8_t* ptile = sP + (c >> 1) * ATT_TILE_BYTES;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 pk;
@@ -247,39 +251,33 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pk.y = pack_bf16x2(pe[g * 8 + 2], pe[g * 8 + 3]);
           pk.z = pack_bf16x2(pe[g * 8 + 4], pe[g * 8 + 5]);
           pk.w = pack_bf16x2(pe[g * 8 + 6], pe[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(ptile + sw128_offset(row, (c & 1) * 4 + g)) = pk;
+          *reinterpret_cast<uint4*>(ptile + sw128_offset(row, cc * 4 + g)) = pk;
         }
       }
-      l_run = l_run * alpha + l_tile;
+      l_run = fmaf(l_run, alpha, l_tile);  // partial sum over my 64 columns; halves are added at the end
       m_run = m_new;
       alpha_prev = alpha;
-      // P (generic-proxy stores) -> visible to the tensor core (async proxy); S reads are complete
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      // note: o_acc still lacks alpha for THIS tile; it is applied when P V of this tile is added
-      // (alpha_prev), i.e. o = o*alpha_j + PV_j.
     }
 
     if (n_tiles > 0) {
       mbar_wait(pv_full, (n_tiles - 1) & 1);
       tc_fence_after_sync();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(tmem_PV + lane_sel + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = o_acc[c * 32 + e] * alpha_prev + __uint_as_float(r[e]);
-      }
+      add_pv(alpha_prev);
     }
+    // total row sum = both halves (the P staging tile is free now: every P V has completed)
+    float* lx = reinterpret_cast<float*>(sP);
+    lx[half * 128 + row] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float l_tot = lx[row] + lx[128 + row];
     if (qi < p.n_q) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* dst = p.o + ((long long)batch * p.n_q + qi) * p.ldo + head * ATT_D;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      __nv_bfloat16* dst = p.o + ((long long)batch * p.n_q + qi) * p.ldo + head * ATT_D + half * 32;
 #pragma unroll
-      for (int g = 0; g < ATT_D / 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 pk;
         pk.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
         pk.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
@@ -287,8 +285,8 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         pk.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
         *reinterpret_cast<uint4*>(dst + g * 8) = pk;
       }
-      if (p.lse != nullptr) {
-        const float lse = l_run > 0.f ? (m_run + log2f(l_run)) : INFINITY;  // log2 domain (x ln2 = natural)
+      if (p.lse != nullptr && half == 0) {
+        const float lse = l_tot > 0.f ? (m_run + log2f(l_tot)) : INFINITY;  // log2 domain (x ln2 = natural)
         p.lse[((long long)batch * p.h + head) * p.lse_stride + qi] = lse;
       }
     }
@@ -297,7 +295,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  if (warp == 5) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  if (warp == ATT_MMA_WARP) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
 }
 
 }  // namespace alm

@@ -18,6 +18,7 @@ struct GemmParams {
   int M, N, K, batch;
   int m_blocks, n_blocks, k_blocks, split_k;
   int c_fp32, acc_mode;
+  int tma_store;  // bf16 overwrite outputs: stage through smem and store with TMA (full 128-B lines)
   float alpha;
 };
 
@@ -31,20 +32,23 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 2 * GEMM_BLOCK_M * 128;  // two [128 rows x 128 B] SW128 output tiles
+  static constexpr int SMEM_BYTES =
+      STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint8_t* smem_c = smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES);  // epilogue staging (TMA store)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;                  // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]  MMA -> TMA
   uint64_t* acc_full_bar = bars + 2 * STAGES; // [2]       MMA -> epilogue
@@ -179,6 +183,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const bool row_ok = gm < p.M;
       const long long row_off = (long long)b * p.strideC + (long long)gm * p.ldc;
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
+      if (p.tma_store) {
+        // TMEM -> registers -> bf16 -> SW128 smem tile -> cp.async.bulk.tensor store (tails clipped by TMA)
+        const bool leader = (warp == 4 && lane == 0);
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+          uint8_t* stage_c = smem_c + (cc & 1) * (GEMM_BLOCK_M * 128);
+          if (leader) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + cc * 64, r0);
+          tmem_ld_32x32b_x32(taddr + cc * 64 + 32, r1);
+          tmem_ld_wait();
+          if (cc == BLOCK_N / 64 - 1) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r0[g * 8 + 0]) * p.alpha, __uint_as_float(r0[g * 8 + 1]) * p.alpha);
+            o.y = pack_bf16x2(__uint_as_float(r0[g * 8 + 2]) * p.alpha, __uint_as_float(r0[g * 8 + 3]) * p.alpha);
+            o.z = pack_bf16x2(__uint_as_float(r0[g * 8 + 4]) * p.alpha, __uint_as_float(r0[g * 8 + 5]) * p.alpha);
+            o.w = pack_bf16x2(__uint_as_float(r0[g * 8 + 6]) * p.alpha, __uint_as_float(r0[g * 8 + 7]) * p.alpha);
+            *reinterpret_cast<uint4*>(stage_c + sw128_offset(row, g)) = o;
+            o.x = pack_bf16x2(__uint_as_float(r1[g * 8 + 0]) * p.alpha, __uint_as_float(r1[g * 8 + 1]) * p.alpha);
+            o.y = pack_bf16x2(__uint_as_float(r1[g * 8 + 2]) * p.alpha, __uint_as_float(r1[g * 8 + 3]) * p.alpha);
+            o.z = pack_bf16x2(__uint_as_float(r1[g * 8 + 4]) * p.alpha, __uint_as_float(r1[g * 8 + 5]) * p.alpha);
+            o.w = pack_bf16x2(__uint_as_float(r1[g * 8 + 6]) * p.alpha, __uint_as_float(r1[g * 8 + 7]) * p.alpha);
+            *reinterpret_cast<uint4*>(stage_c + sw128_offset(row, 4 + g)) = o;
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader && n0 + cc * 64 < p.N) {
+            tma_store_3d(&tmC, stage_c, n0 + cc * 64, mb * GEMM_BLOCK_M, b);
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
@@ -250,6 +294,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
+  if (p.tma_store && warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -257,7 +302,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
   static bool attr_set = false;
@@ -267,7 +313,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total = p.m_blocks * p.n_blocks * p.split_k * p.batch;
   const int grid = total < num_sms() ? total : num_sms();
-  kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kfn<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;
@@ -347,10 +393,23 @@ extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strid
     if (rc != ALM_OK) return rc;
   }
 
+  // bf16 overwrite outputs with 16-B aligned rows take the smem-staged TMA-store epilogue
+  CUtensorMap tmC = tmA;
+  p.tma_store = 0;
+  if (!c_fp32 && acc_mode == 0 && bias == nullptr && ldc % 8 == 0 && (batch == 1 || strideC % 8 == 0) &&
+      (reinterpret_cast<uintptr_t>(C) & 15u) == 0) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
+    uint64_t strides[3] = {2, (uint64_t)ldc * 2, batch > 1 ? (uint64_t)strideC * 2 : (uint64_t)M * ldc * 2};
+    uint32_t box[3] = {64, GEMM_BLOCK_M, 1};
+    int rc = make_tensor_map(&tmC, C, 2, 3, dims, strides, box, true);
+    if (rc != ALM_OK) return rc;
+    p.tma_store = 1;
+  }
+
 #define ALM_GEMM_DISPATCH(BN_)                                                             \
-  if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(tmA, tmB, p, stream);          \
-  if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, p, stream);            \
-  return launch_gemm<BN_, true, true>(tmA, tmB, p, stream);
+  if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(tmA, tmB, tmC, p, stream);     \
+  if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, tmC, p, stream);       \
+  return launch_gemm<BN_, true, true>(tmA, tmB, tmC, p, stream);
   if (BN == 256) { ALM_GEMM_DISPATCH(256) }
   if (BN == 128) { ALM_GEMM_DISPATCH(128) }
   { ALM_GEMM_DISPATCH(64) }

@@ -48,6 +48,16 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pk(f[0], f[1]), pk(f[2], f[3]), pk(f[4], f[5]), pk(f[6], f[7]));
 }
 
+__device__ __forceinline__ void lds4(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));  // MUFU.TANH, rel. err ~2^-11: far below the bf16 noise floor
+  return y;
+}
+
 struct Params {
   const float* gamma_hc; const float* dyn_alpha; const float* dyn_beta; const float* static_alpha;
   const float* static_beta; const float* alpha_scale; const float* beta_scale; const float* ln_gamma;
@@ -154,19 +164,22 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
     for (int k = 0; k < NCH; ++k) {
       if (act[k]) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = ch[k] + e;
-          const float g1 = sG1[c], bf = sBf[c];
-          float av[T];
+        for (int h4 = 0; h4 < 2; ++h4) {  // 4 channels at a time: 16-B shared loads, no bank-conflict replays
+          const int c = ch[k] + h4 * 4;
+          float g1[4], bf[4], av[T][4];
+          lds4(sG1 + c, g1);
+          lds4(sBf + c, bf);
 #pragma unroll
-          for (int t = 0; t < T; ++t) av[t] = sA[t * d + c];
+          for (int t = 0; t < T; ++t) lds4(sA + t * d + c, av[t]);
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            const float nv = R[s][k][e] * inv[s] * g1;
+          for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int t = 0; t < T; ++t) w[s * T + t] = fmaf(nv, av[t], w[s * T + t]);
-            w[S * T + s] = fmaf(nv, bf, w[S * T + s]);
-          }
+            for (int s = 0; s < S; ++s) {
+              const float nv = R[s][k][h4 * 4 + e] * inv[s] * g1[e];
+#pragma unroll
+              for (int t = 0; t < T; ++t) w[s * T + t] = fmaf(nv, av[t][e], w[s * T + t]);
+              w[S * T + s] = fmaf(nv, bf[e], w[S * T + s]);
+            }
         }
       }
     }
@@ -176,10 +189,10 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
     for (int s = 0; s < S; ++s) {
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        w[s * T + t] = tanhf(w[s * T + t]);
+        w[s * T + t] = tanh_fast(w[s * T + t]);
         alpha[s][t] = fmaf(w[s * T + t], a_scale, Astat[s][t]);
       }
-      w[S * T + s] = tanhf(w[S * T + s]);
+      w[S * T + s] = tanh_fast(w[S * T + s]);
       beta[s] = fmaf(w[S * T + s], b_scale, Bstat[s]);
     }
     // mixed residual streams out; branch input kept for the LayerNorm
@@ -225,9 +238,11 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
       if (act[k]) {
-        float o[8];
+        float o[8], lg[8];
+        lds4(sLn + ch[k], lg);
+        lds4(sLn + ch[k] + 4, lg + 4);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (bi[k][e] - mean) * rstd * sLn[ch[k] + e];
+        for (int e = 0; e < 8; ++e) o[e] = (bi[k][e] - mean) * rstd * lg[e];
         *reinterpret_cast<uint4*>(xn + (size_t)m * d + ch[k]) = pack8(o);
       }
     if (lt == 0) {
@@ -246,7 +261,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// smem for the backward adds gradient accumulators: [8d, 16d): gG, gBf, gLn, gA[T]  (same order as params)
+// smem for the backward adds PRIVATE per-slot gradient accumulators [TOK][8][d]: gG, gBf, gLn, gA[T]
 template <int NCH>
 __global__ void __launch_bounds__(THREADS, 1)
 pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __restrict__ Y,
@@ -257,20 +272,21 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
                float* __restrict__ dbeta_prev, float* __restrict__ dx_expand, float dx_scale, Grads gr, int M,
                int d) {
   extern __shared__ float sm[];
-  float* sGrad = sm + 8 * d;         // [8][d]
-  float* mailbox = sm + 16 * d;      // [TOK][2][2][24]
+  float* sGradAll = sm + 8 * d;              // [TOK][8][d]: private per token slot -> plain RMW, no atomics
+  float* mailbox = sm + (8 + 8 * TOK) * d;   // [TOK][2][2][24]
   stage_params(sm, prm, d);
-  for (int i = threadIdx.x; i < 8 * d; i += blockDim.x) sGrad[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * TOK * d; i += blockDim.x) sGradAll[i] = 0.f;
   __syncthreads();
   const float* sG1 = sm;
   const float* sBf = sm + d;
   const float* sLn = sm + 2 * d;
   const float* sA = sm + 3 * d;
+  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
+  float* sGrad = sGradAll + (size_t)slot * 8 * d;
   float* gG = sGrad;
   float* gBf = sGrad + d;
   float* gLn = sGrad + 2 * d;
   float* gA = sGrad + 3 * d;
-  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
   float* mail = mailbox + slot * (2 * 2 * 24);
   int which = 0;
   const int bar_id = 1 + slot;
@@ -335,20 +351,26 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         for (int s = 0; s < S; ++s)
           unpack8(*reinterpret_cast<const uint4*>(dR_out + ((size_t)m * S + s) * d + ch[k]), dmix[s + 1][k]);
         // LayerNorm backward, part 1 (dmix[0] temporarily holds gl = dxn * ln_gamma)
-        float dx8[8];
+        float dx8[8], lg[8], gl8[8];
         unpack8(*reinterpret_cast<const uint4*>(dxn + (size_t)m * d + ch[k]), dx8);
+        lds4(sLn + ch[k], lg);
+        lds4(sLn + ch[k] + 4, lg + 4);
+        lds4(gLn + ch[k], gl8);
+        lds4(gLn + ch[k] + 4, gl8 + 4);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float b = 0.f;
 #pragma unroll
           for (int s = 0; s < S; ++s) b = fmaf(alpha[s][0], R[s][k][e], b);
           const float xhat = (b - mean) * rstd;
-          const float gl = dx8[e] * sLn[ch[k] + e];
-          atomicAdd(&gLn[ch[k] + e], dx8[e] * xhat);
+          const float gl = dx8[e] * lg[e];
+          gl8[e] = fmaf(dx8[e], xhat, gl8[e]);
           lnred[0] += gl;
           lnred[1] = fmaf(gl, xhat, lnred[1]);
           dmix[0][k][e] = gl;
         }
+        *reinterpret_cast<float4*>(gLn + ch[k]) = make_float4(gl8[0], gl8[1], gl8[2], gl8[3]);
+        *reinterpret_cast<float4*>(gLn + ch[k] + 4) = make_float4(gl8[4], gl8[5], gl8[6], gl8[7]);
       } else {
 #pragma unroll
         for (int s = 0; s < S; ++s)
@@ -410,35 +432,45 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
     for (int k = 0; k < NCH; ++k) {
       if (act[k]) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = ch[k] + e;
-          const float g1 = sG1[c], bf = sBf[c];
-          float av[T], dm[T];
+        for (int h4 = 0; h4 < 2; ++h4) {
+          const int c = ch[k] + h4 * 4;
+          float g1[4], bf[4], av[T][4], pG[4], pBf[4], pA[T][4];
+          lds4(sG1 + c, g1);
+          lds4(sBf + c, bf);
+          lds4(gG + c, pG);
+          lds4(gBf + c, pBf);
 #pragma unroll
-          for (int t = 0; t < T; ++t) { av[t] = sA[t * d + c]; dm[t] = dmix[t][k][e]; }
-          float pG = 0.f, pBf = 0.f, pA[T] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int t = 0; t < T; ++t) { lds4(sA + t * d + c, av[t]); lds4(gA + t * d + c, pA[t]); }
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            float acc = 0.f;
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int e = h4 * 4 + e4;
+            float dm[T];
 #pragma unroll
-            for (int t = 0; t < T; ++t) acc = fmaf(alpha[s][t], dm[t], acc);
-            float dn = dwb[s] * bf;
+            for (int t = 0; t < T; ++t) dm[t] = dmix[t][k][e];
 #pragma unroll
-            for (int t = 0; t < T; ++t) dn = fmaf(dwa[s][t], av[t], dn);
-            const float rn = R[s][k][e] * inv[s];
-            const float nv = rn * g1;
-            pG = fmaf(dn * rn, sqrt_d, pG);
-            pBf = fmaf(nv, dwb[s], pBf);
+            for (int s = 0; s < S; ++s) {
+              float acc = 0.f;
 #pragma unroll
-            for (int t = 0; t < T; ++t) pA[t] = fmaf(nv, dwa[s][t], pA[t]);
-            const float u = dn * g1;
-            udot[s] = fmaf(u, R[s][k][e], udot[s]);
-            dmix[s][k][e] = fmaf(u, inv[s], acc);  // dR[s] (dm[] was read above)
+              for (int t = 0; t < T; ++t) acc = fmaf(alpha[s][t], dm[t], acc);
+              float dn = dwb[s] * bf[e4];
+#pragma unroll
+              for (int t = 0; t < T; ++t) dn = fmaf(dwa[s][t], av[t][e4], dn);
+              const float rn = R[s][k][e] * inv[s];
+              const float nv = rn * g1[e4];
+              pG[e4] = fmaf(dn * rn, sqrt_d, pG[e4]);
+              pBf[e4] = fmaf(nv, dwb[s], pBf[e4]);
+#pragma unroll
+              for (int t = 0; t < T; ++t) pA[t][e4] = fmaf(nv, dwa[s][t], pA[t][e4]);
+              const float u = dn * g1[e4];
+              udot[s] = fmaf(u, R[s][k][e], udot[s]);
+              dmix[s][k][e] = fmaf(u, inv[s], acc);  // dR[s] (dm[] was read above)
+            }
           }
-          atomicAdd(&gG[c], pG);
-          atomicAdd(&gBf[c], pBf);
+          *reinterpret_cast<float4*>(gG + c) = make_float4(pG[0], pG[1], pG[2], pG[3]);
+          *reinterpret_cast<float4*>(gBf + c) = make_float4(pBf[0], pBf[1], pBf[2], pBf[3]);
 #pragma unroll
-          for (int t = 0; t < T; ++t) atomicAdd(&gA[t * d + c], pA[t]);
+          for (int t = 0; t < T; ++t)
+            *reinterpret_cast<float4*>(gA + t * d + c) = make_float4(pA[t][0], pA[t][1], pA[t][2], pA[t][3]);
         }
       }
     }
@@ -493,11 +525,18 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   }
   __syncthreads();
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(gr.gamma_hc + i, gG[i]);
-    atomicAdd(gr.dyn_beta + i, gBf[i]);
-    atomicAdd(gr.ln_gamma + i, gLn[i]);
+    float acc[8];
 #pragma unroll
-    for (int t = 0; t < T; ++t) atomicAdd(gr.dyn_alpha + (size_t)i * T + t, gA[t * d + i]);
+    for (int a8 = 0; a8 < 8; ++a8) {
+      acc[a8] = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < TOK; ++sl) acc[a8] += sGradAll[((size_t)sl * 8 + a8) * d + i];
+    }
+    atomicAdd(gr.gamma_hc + i, acc[0]);
+    atomicAdd(gr.dyn_beta + i, acc[1]);
+    atomicAdd(gr.ln_gamma + i, acc[2]);
+#pragma unroll
+    for (int t = 0; t < T; ++t) atomicAdd(gr.dyn_alpha + (size_t)i * T + t, acc[3 + t]);
   }
   if (lt == 0) {  // one thread per token slot holds that slot's scalar-parameter partial sums
 #pragma unroll
@@ -510,7 +549,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
 }
 
 inline size_t fwd_smem(int d) { return (size_t)(8 * d + TOK * 2 * 2 * 24) * sizeof(float); }
-inline size_t bwd_smem(int d) { return (size_t)(16 * d + TOK * 2 * 2 * 24) * sizeof(float); }
+inline size_t bwd_smem(int d) { return (size_t)((8 + 8 * TOK) * d + TOK * 2 * 2 * 24) * sizeof(float); }
 
 }  // namespace hc2
 }  // namespace alm

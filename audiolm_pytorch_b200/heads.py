@@ -27,6 +27,9 @@ class HeadCache:
     def __init__(self):
         self._pk = _PackedWeights()
 
+    def clear(self):
+        self._pk.clear()
+
     def linear(self, x2d, weight, bias, key):
         packed = self._pk.get(key, [weight], lambda: pack_head(weight))
         V = weight.shape[0]

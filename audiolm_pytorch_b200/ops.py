@@ -350,3 +350,15 @@ def rvq_decode(indices, codebooks):
     out = torch.empty(N, D, device=indices.device, dtype=f32)
     _lib.call("alm_rvq_decode", indices, Q, codebooks.contiguous(), out, D, N, D, C, Q)
     return out
+
+
+def topk_gumbel_sample(logits, uniform, *, k, temperature=1.0):
+    """ids [R] = Gumbel-max sample over the k largest logits of each row (noise supplied by the caller)."""
+    _check_cuda(logits, uniform)
+    assert logits.dtype == f32 and uniform.dtype == f32 and logits.shape == uniform.shape
+    assert logits.stride(-1) == 1 and uniform.stride(-1) == 1
+    R, V = logits.shape
+    ids = torch.empty(R, device=logits.device, dtype=torch.int64)
+    _lib.call("alm_topk_gumbel_sample", logits, logits.stride(0), uniform, uniform.stride(0), ids, R, V, int(k),
+              float(temperature))
+    return ids

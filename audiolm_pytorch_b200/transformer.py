@@ -142,6 +142,9 @@ class _PackedWeights:
     def __init__(self):
         self._cache = {}
 
+    def clear(self):
+        self._cache.clear()
+
     def get(self, key, params, build):
         ver = tuple((p.data_ptr(), p._version) for p in params)
         hit = self._cache.get(key)
@@ -248,6 +251,10 @@ class Transformer(nn.Module):
             ]))
         self.norm = LayerNorm(dim)
         self._packed = _PackedWeights()
+
+    def invalidate_weight_cache(self):
+        """drop the bf16 operand copies (they are rebuilt on the next forward, as autocast re-casts weights)."""
+        self._packed.clear()
 
     # ---- parameter plumbing ------------------------------------------------------------------
     def _param_list(self):

@@ -211,6 +211,10 @@ def main_ours(args):
 
     def step(sem, coarse):
         bucket.zero_()
+        # a real training step sees new weights every iteration: rebuild the bf16 operand copies inside the
+        # timed region (what bf16 autocast does at every Linear) instead of reusing last step's cache
+        model.transformer.invalidate_weight_cache()
+        model._heads.clear()
         coarse_labels = torch.cat((coarse, eos), dim=1)
         sl, cl = model(semantic_token_ids=sem, coarse_token_ids=coarse)
         ls = cross_entropy(sl, sem)

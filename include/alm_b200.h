@@ -132,6 +132,13 @@ int alm_ce_fwd_bwd(const float* logits, int64_t ldl, const int64_t* labels, int6
                    void* dlogits, int64_t ldd, const float* scale_num, const float* scale_den, int rows, int V,
                    int Vpad, alm_stream_t stream);
 
+/* ---- sampling: top-k filter + Gumbel-max in one launch ------------------------------------------- */
+/* ids[r] = argmax_c over the k largest logits of row r of (logits/temperature - log(-log(u+1e-20)+1e-20));
+ * `uniform` is drawn by the caller (torch `uniform_`, same generator order as the reference) so sampled ids
+ * are reproducible.  Replaces top_k + gumbel_sample (audiolm_pytorch.py:98-117) in the generate loops. */
+int alm_topk_gumbel_sample(const float* logits, int64_t ldl, const float* uniform, int64_t ldu, int64_t* ids, int rows,
+                           int V, int k, float temperature, alm_stream_t stream);
+
 /* ---- small helpers on the same path ------------------------------------------------------------- */
 /* out = alpha*x + beta*y (bf16, 2-D strided): value-residual mix v = 0.5 (v + v_first), :355-358 */
 int alm_axpby_bf16(const void* x, int64_t ldx, float alpha, const void* y, int64_t ldy, float beta, void* out,
