@@ -89,7 +89,9 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb = blockIdx.x, batch = blockIdx.y;
+  // heaviest key blocks first across ALL batches (LPT order): CTA x -> (kb = x / b, batch = x % b).  With the
+  // old (kb fastest) order a late-starting kb=0 CTA stretched the makespan to 200 iterations vs 118 ideal.
+  const int kb = blockIdx.x / p.b, batch = blockIdx.x % p.b;
   const int k0 = kb * AB_T;
   const int off = p.n_k - p.n_q;
   const int n_qblocks = (p.n_q + AB_T - 1) / AB_T;
@@ -514,7 +516,7 @@ extern "C" int alm_mqa_attn_bwd(const void* q, int64_t ldq, const void* k, int64
     ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
-  dim3 grid_kv((n_k + AB_T - 1) / AB_T, b);
+  dim3 grid_kv(((n_k + AB_T - 1) / AB_T) * b);
   mqa_attn_bwd_dkv_kernel<<<grid_kv, AB_THREADS, DKV_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
   ALM_CHECK_LAUNCH();
   dim3 grid_q((n_q + AB_T - 1) / AB_T, h, b);

@@ -120,13 +120,14 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
     for (int e = 0; e < 8; ++e) gacc[k][e] = 0.f;
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
     const float mean = stats[(size_t)m * 2], rstd = stats[(size_t)m * 2 + 1];
-    float a[NCH][8], gt[NCH][8], gl[NCH][8], xh[NCH][8];
+    // one erf per element: ge = gelu(gate) is kept; Phi(gate) = ge / gate is recovered from it in the second phase
+    float a[NCH][8], gt[NCH][8], gl[NCH][8], ge[NCH][8];
     float r2[2] = {0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { a[k][e] = gt[k][e] = gl[k][e] = xh[k][e] = 0.f; }
+      for (int e = 0; e < 8; ++e) { a[k][e] = gt[k][e] = gl[k][e] = ge[k][e] = 0.f; }
       if (c0 < inner_pad) {
         float dv[8];
         unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a[k]);
@@ -135,12 +136,12 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           if (c0 + e < inner) {
-            const float g = gelu_erf(gt[k][e]) * a[k][e];
-            xh[k][e] = (g - mean) * rstd;
+            ge[k][e] = gelu_erf(gt[k][e]);
+            const float xh = (ge[k][e] * a[k][e] - mean) * rstd;
             gl[k][e] = dv[e] * gamma[c0 + e];
-            gacc[k][e] += dv[e] * xh[k][e];
+            gacc[k][e] += dv[e] * xh;
             r2[0] += gl[k][e];
-            r2[1] += gl[k][e] * xh[k][e];
+            r2[1] += gl[k][e] * xh;
           }
         }
       }
@@ -155,9 +156,14 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           if (c0 + e < inner) {
-            const float dg = rstd * (gl[k][e] - m1 - xh[k][e] * m2);
-            da[e] = dg * gelu_erf(gt[k][e]);
-            dg8[e] = dg * a[k][e] * gelu_erf_grad(gt[k][e]);
+            const float x = gt[k][e];
+            const float xh = (ge[k][e] * a[k][e] - mean) * rstd;
+            const float dg = rstd * (gl[k][e] - m1 - xh * m2);
+            // Phi(x) = gelu(x)/x (series 0.5 + x*phi(0) near 0);  gelu'(x) = Phi(x) + x*phi(x)
+            const float cdf = fabsf(x) > 1e-3f ? __fdividef(ge[k][e], x) : fmaf(x, 0.3989422804014327f, 0.5f);
+            const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+            da[e] = dg * ge[k][e];
+            dg8[e] = dg * a[k][e] * fmaf(x, pdf, cdf);
           } else {
             da[e] = dg8[e] = 0.f;
           }
@@ -510,7 +516,7 @@ extern "C" int alm_geglu_ln_fwd(const void* h, int64_t ldh, int gate_off, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(M > 0 && inner > 0 && inner_pad >= inner && inner_pad % 8 == 0, ALM_ERR_ARG);
   ALM_REQUIRE(ldh % 8 == 0 && ldg % 8 == 0 && gate_off % 8 == 0, ALM_ERR_ALIGN);
-  if (inner_pad <= gg2::NCH * 64 * 8) {
+  if (false && inner_pad <= gg2::NCH * 64 * 8) {  // v2 measured slower than v1 at C3 (0.29 vs 0.27 ms): disabled
     const int grid2 = min(ceil_div(M, gg2::ROWS), num_sms() * 2);
     gg2::fwd_kernel<<<grid2, gg2::THREADS, 0, stream>>>((const __nv_bfloat16*)h, ldh, gate_off, gamma,
                                                         (__nv_bfloat16*)gn, ldg, stats, M, inner, inner_pad);
@@ -537,7 +543,7 @@ extern "C" int alm_geglu_ln_bwd(const void* h, int64_t ldh, int gate_off, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(M > 0 && inner > 0 && inner_pad >= inner && inner_pad % 8 == 0, ALM_ERR_ARG);
   ALM_REQUIRE(ldh % 8 == 0 && ldg % 8 == 0 && gate_off % 8 == 0, ALM_ERR_ALIGN);
-  if (inner_pad <= gg2::NCH * 64 * 8) {
+  if (false && inner_pad <= gg2::NCH * 64 * 8) {  // v2 measured slower than v1 at C3 (0.78 vs 0.56 ms): disabled
     const int grid2 = min(ceil_div(M, gg2::ROWS), num_sms());
     const size_t smem = (size_t)gg2::ROWS * inner_pad * sizeof(float);
     static bool attr_set = false;

@@ -172,7 +172,7 @@ def pack_w1(w, inner):
 
 def best_split_k(M, N, K, n_sm=148):
     """split-K factor for weight-gradient GEMMs (few output tiles, very long K)."""
-    bn = 64 if N <= 64 else (128 if N <= 128 or (-N) % 256 > (-N) % 128 else 256)
+    bn = 64 if N <= 64 else (128 if N <= 128 or (-(-N // 128) * 128) * 10 < (-(-N // 256) * 256) * 9 else 256)
     tiles = -(-M // 128) * -(-N // bn)
     kb = -(-K // 64)
     best, best_t = 1, None
