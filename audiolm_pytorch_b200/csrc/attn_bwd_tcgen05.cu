@@ -18,8 +18,8 @@ namespace alm {
 constexpr int AB_T = 128;                     // tile edge (queries or keys)
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;      // 16 KB
-constexpr int AB_THREADS = 320;          // warps 0-7 compute (2 per TMEM lane quadrant), 8 TMA, 9 MMA
-constexpr int AB_TMA_WARP = 8, AB_MMA_WARP = 9;
+constexpr int AB_THREADS = 576;          // warps 0-15 compute (4 per TMEM lane quadrant), 16 TMA, 17 MMA
+constexpr int AB_TMA_WARP = 16, AB_MMA_WARP = 17;
 constexpr int AB_STAGES = 2;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -105,7 +105,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(kv_full, 1);
     for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 8);
+    mbar_init(p_full, 16);
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -183,9 +183,9 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   } else {
-    // compute warps: thread == key row; warps w and w+4 share a TMEM lane quadrant and split the 128 query
-    // columns in two halves (more warps in flight per SM, half the serial work per thread)
-    const int quad = warp & 3, half = warp >> 2;
+    // compute warps: thread == key row; the 4 warps {q, q+4, q+8, q+12} share TMEM lane quadrant q and each
+    // owns one 32-query column chunk (16 warps in flight per SM hide the ALU / TMEM-load latencies)
+    const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;
     const int kj = k0 + row;
     const uint32_t lane_sel = uint32_t(quad * 32) << 16;
@@ -203,9 +203,8 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const float* del_s = sDelta + stage * AB_T;
       // whole tile below the causal diagonal and inside n_q: only the per-row key flag matters
       const bool tile_full = (q0 + AB_T <= p.n_q) && (!p.causal || k0 + AB_T - 1 <= q0 + off);
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      {
+        const int c = part;
         uint32_t rs[32], rp[32];
         __syncwarp();
         tmem_ld_32x32b_x32(tmem_ST + lane_sel + c * 32, rs);
@@ -239,12 +238,12 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = part >> 1;  // parts 0,1 write dV columns [0,32),[32,64); parts 2,3 write dK
       __nv_bfloat16* dst = (which == 0 ? p.dv : p.dk) +
                            ((size_t)batch * p.n_k + (kj < p.n_k ? kj : 0)) * (which == 0 ? p.lddv : p.lddk);
       {
-        const int c = half;
+        const int c = part & 1;
         uint32_t r[32];
         if (n_iter > 0) {
           __syncwarp();
@@ -314,7 +313,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(q_full, 1);
     for (int i = 0; i < AB_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 8);
+    mbar_init(p_full, 16);
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -382,7 +381,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
   } else {
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;
     const int qi = q0 + row;
     const uint32_t lane_sel = uint32_t(quad * 32) << 16;
@@ -397,9 +396,8 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int kbase = j * AB_T;
       const bool tile_full = mrow == nullptr && (q0 + AB_T <= p.n_q) && (kbase + AB_T <= p.n_k) &&
                              (!p.causal || kbase + AB_T - 1 <= q0 + off);
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      {
+        const int c = part;
         uint32_t rs[32], rp[32];
         __syncwarp();
         tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, rs);
@@ -432,8 +430,8 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
-    {
-      const int c = half;
+    if (part < 2) {
+      const int c = part;
       uint32_t r[32];
       if (n_tiles > 0) {
         __syncwarp();

@@ -651,18 +651,17 @@ extern "C" int alm_hc_pre_fwd(const void* R_in, const void* Y, const float* beta
   ALM_REQUIRE(streams == HC_S, ALM_ERR_UNSUPPORTED);
   ALM_REQUIRE(d % 8 == 0 && d >= 8 && d <= 8192 && M > 0, ALM_ERR_ARG);
   ALM_REQUIRE((x_expand != nullptr) != (R_in != nullptr), ALM_ERR_ARG);
-  if (d <= 1024) {  // second-generation kernel: 2 warps per token, no CTA-wide barriers
+  if (d <= 1024) {  // second-generation kernel: 2 or 4 warps per token, no CTA-wide barriers
     hc2::Params p2{gamma_hc, dyn_alpha, dyn_beta, static_alpha, static_beta, alpha_scale, beta_scale, ln_gamma};
-    const int grid = min(ceil_div(M, hc2::TOK), num_sms() * 2);
-    const size_t smem = hc2::fwd_smem(d);
-    if (d <= 512)
-      hc2::pre_fwd_kernel<1><<<grid, hc2::THREADS, smem, stream>>>(
-          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, (__nv_bfloat16*)R_out,
-          (__nv_bfloat16*)bin, (__nv_bfloat16*)xn, beta_out, aux, M, d);
-    else
-      hc2::pre_fwd_kernel<2><<<grid, hc2::THREADS, smem, stream>>>(
-          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, (__nv_bfloat16*)R_out,
-          (__nv_bfloat16*)bin, (__nv_bfloat16*)xn, beta_out, aux, M, d);
+    const int tpt = 64;  // 4 warps per token (tpt 128) measured slower at d=1024: 297 vs 227 us
+    const int tok = hc2::THREADS / tpt;
+    const int grid = min(ceil_div(M, tok), num_sms() * 2);
+    const size_t smem = hc2::fwd_smem(d, tpt);
+#define HC2_FWD_ARGS (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, (__nv_bfloat16*)R_out, \
+                     (__nv_bfloat16*)bin, (__nv_bfloat16*)xn, beta_out, aux, M, d
+    if (d <= 512) hc2::pre_fwd_kernel<1, 64><<<grid, hc2::THREADS, smem, stream>>>(HC2_FWD_ARGS);
+    else hc2::pre_fwd_kernel<2, 64><<<grid, hc2::THREADS, smem, stream>>>(HC2_FWD_ARGS);
+#undef HC2_FWD_ARGS
     ALM_CHECK_LAUNCH();
     ALM_LAUNCHED(1);
     return ALM_OK;
@@ -693,26 +692,24 @@ extern "C" int alm_hc_pre_bwd(const void* R_in, const void* Y, const float* beta
     hc2::Params p2{gamma_hc, dyn_alpha, dyn_beta, static_alpha, static_beta, alpha_scale, beta_scale, ln_gamma};
     hc2::Grads g2{g_gamma_hc, g_dyn_alpha, g_dyn_beta, g_static_alpha, g_static_beta, g_alpha_scale, g_beta_scale,
                   g_ln_gamma};
-    const int grid2 = min(ceil_div(M, hc2::TOK), num_sms());
-    const size_t smem = hc2::bwd_smem(d);
+    const int tpt = 64;  // tpt 128 (4 warps per token, 2 CTAs/SM, 128-register cap) measured slower: 883 vs 713 us
+    const int tok = hc2::THREADS / tpt;
+    const int grid2 = min(ceil_div(M, tok), num_sms());
+    const size_t smem = hc2::bwd_smem(d, tpt);
     static bool attr_set = false;
     if (!attr_set) {
-      ALM_CUDA_OK(cudaFuncSetAttribute(hc2::pre_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)hc2::bwd_smem(512)));
-      ALM_CUDA_OK(cudaFuncSetAttribute(hc2::pre_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)hc2::bwd_smem(1024)));
+      ALM_CUDA_OK(cudaFuncSetAttribute(hc2::pre_bwd_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)hc2::bwd_smem(512, 64)));
+      ALM_CUDA_OK(cudaFuncSetAttribute(hc2::pre_bwd_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)hc2::bwd_smem(1024, 64)));
       attr_set = true;
     }
-    if (d <= 512)
-      hc2::pre_bwd_kernel<1><<<grid2, hc2::THREADS, smem, stream>>>(
-          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, aux,
-          (const __nv_bfloat16*)dR_out, (const __nv_bfloat16*)dxn, (const __nv_bfloat16*)dbin_extra, dbeta,
-          (__nv_bfloat16*)dR_in, (__nv_bfloat16*)dY, dbeta_prev, dx_expand, dx_scale, g2, M, d);
-    else
-      hc2::pre_bwd_kernel<2><<<grid2, hc2::THREADS, smem, stream>>>(
-          (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, aux,
-          (const __nv_bfloat16*)dR_out, (const __nv_bfloat16*)dxn, (const __nv_bfloat16*)dbin_extra, dbeta,
-          (__nv_bfloat16*)dR_in, (__nv_bfloat16*)dY, dbeta_prev, dx_expand, dx_scale, g2, M, d);
+#define HC2_BWD_ARGS (const __nv_bfloat16*)R_in, (const __nv_bfloat16*)Y, beta_prev, x_expand, p2, aux,              \
+                     (const __nv_bfloat16*)dR_out, (const __nv_bfloat16*)dxn, (const __nv_bfloat16*)dbin_extra, dbeta, \
+                     (__nv_bfloat16*)dR_in, (__nv_bfloat16*)dY, dbeta_prev, dx_expand, dx_scale, g2, M, d
+    if (d <= 512) hc2::pre_bwd_kernel<1, 64><<<grid2, hc2::THREADS, smem, stream>>>(HC2_BWD_ARGS);
+    else hc2::pre_bwd_kernel<2, 64><<<grid2, hc2::THREADS, smem, stream>>>(HC2_BWD_ARGS);
+#undef HC2_BWD_ARGS
     ALM_CHECK_LAUNCH();
     ALM_LAUNCHED(1);
     return ALM_OK;

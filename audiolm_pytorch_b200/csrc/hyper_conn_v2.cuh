@@ -13,26 +13,34 @@ namespace alm {
 namespace hc2 {
 
 constexpr int S = 4, T = 5;
-constexpr int TOK = 4;            // token slots per CTA
-constexpr int THREADS = 64 * TOK;
+constexpr int THREADS = 256;      // a CTA holds THREADS / TPT token slots; TPT = threads per token (64 or 128)
 constexpr int AUX = S * T + S + S + 2;
 
-__device__ __forceinline__ void bar64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+template <int TPT>
+__device__ __forceinline__ void bar_slot(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TPT) : "memory");
+}
 
-// sum N values over the 64 threads of a token slot; all of them get the result.
-template <int N>
-__device__ __forceinline__ void slot_sum(float (&v)[N], float* mail /*[2][2][N_MAX]*/, int& which, int w2, int lane,
+// sum N values over the TPT threads of a token slot; all of them get the result.
+template <int N, int TPT>
+__device__ __forceinline__ void slot_sum(float (&v)[N], float* mail /*[2][TPT/32][24]*/, int& which, int w2, int lane,
                                          int bar_id) {
+  constexpr int WPT = TPT / 32;
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-  float* b = mail + which * (2 * 24);
+  float* b = mail + which * (WPT * 24);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < N; ++i) b[w2 * 24 + i] = v[i];
   }
-  bar64(bar_id);
+  bar_slot<TPT>(bar_id);
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = b[i] + b[24 + i];
+  for (int i = 0; i < N; ++i) {
+    float a = b[i];
+#pragma unroll
+    for (int w = 1; w < WPT; ++w) a += b[w * 24 + i];
+    v[i] = a;
+  }
   which ^= 1;
 }
 
@@ -80,22 +88,23 @@ __device__ __forceinline__ void stage_params(float* sm, const Params& p, int d) 
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NCH>
+template <int NCH, int TPT>
 __global__ void __launch_bounds__(THREADS, 2)
 pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __restrict__ Y,
                const float* __restrict__ beta_prev, const float* __restrict__ x_expand, Params prm,
                __nv_bfloat16* __restrict__ R_out, __nv_bfloat16* __restrict__ bin, __nv_bfloat16* __restrict__ xn,
                float* __restrict__ beta_out, float* __restrict__ aux, int M, int d) {
   extern __shared__ float sm[];
-  float* mailbox = sm + 8 * d;  // [TOK][2][2][24]
+  constexpr int TOK = THREADS / TPT, WPT = TPT / 32;
+  float* mailbox = sm + 8 * d;  // [TOK][2][WPT][24]
   stage_params(sm, prm, d);
   __syncthreads();
   const float* sG1 = sm;
   const float* sBf = sm + d;
   const float* sLn = sm + 2 * d;
   const float* sA = sm + 3 * d;
-  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
-  float* mail = mailbox + slot * (2 * 2 * 24);
+  const int slot = threadIdx.x / TPT, lt = threadIdx.x % TPT, w2 = lt >> 5, lane = lt & 31;
+  float* mail = mailbox + slot * (2 * WPT * 24);
   int which = 0;
   const int bar_id = 1 + slot;
   const float a_scale = *prm.alpha_scale, b_scale = *prm.beta_scale;
@@ -109,7 +118,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   int ch[NCH];
   bool act[NCH];
 #pragma unroll
-  for (int k = 0; k < NCH; ++k) { ch[k] = (lt + 64 * k) * 8; act[k] = ch[k] < d; }
+  for (int k = 0; k < NCH; ++k) { ch[k] = (lt + TPT * k) * 8; act[k] = ch[k] < d; }
 
   for (int m = blockIdx.x * TOK + slot; m < M; m += gridDim.x * TOK) {
     float R[S][NCH][8];
@@ -153,7 +162,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         for (int e = 0; e < 8; ++e) a = fmaf(R[s][k][e], R[s][k][e], a);
       ssq[s] = a;
     }
-    slot_sum<S>(ssq, mail, which, w2, lane, bar_id);
+    slot_sum<S, TPT>(ssq, mail, which, w2, lane, bar_id);
     float inv[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) inv[s] = 1.f / fmaxf(sqrtf(ssq[s]), 1e-12f);
@@ -183,7 +192,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         }
       }
     }
-    slot_sum<S * T + S>(w, mail, which, w2, lane, bar_id);
+    slot_sum<S * T + S, TPT>(w, mail, which, w2, lane, bar_id);
     float alpha[S][T], beta[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -224,7 +233,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         *reinterpret_cast<uint4*>(bin + (size_t)m * d + ch[k]) = pack8(bi[k]);
       }
     }
-    slot_sum<1>(st, mail, which, w2, lane, bar_id);
+    slot_sum<1, TPT>(st, mail, which, w2, lane, bar_id);
     const float mean = st[0] / d;
     float sv[1] = {0.f};
 #pragma unroll
@@ -233,7 +242,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
 #pragma unroll
         for (int e = 0; e < 8; ++e) sv[0] = fmaf(bi[k][e] - mean, bi[k][e] - mean, sv[0]);
       }
-    slot_sum<1>(sv, mail, which, w2, lane, bar_id);
+    slot_sum<1, TPT>(sv, mail, which, w2, lane, bar_id);
     const float rstd = rsqrtf(sv[0] / d + 1e-5f);
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
@@ -262,8 +271,8 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
 
 // ------------------------------------------------------------------------------------------------
 // smem for the backward adds PRIVATE per-slot gradient accumulators [TOK][8][d]: gG, gBf, gLn, gA[T]
-template <int NCH>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NCH, int TPT>
+__global__ void __launch_bounds__(THREADS, TPT == 128 ? 2 : 1)
 pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __restrict__ Y,
                const float* __restrict__ beta_prev, const float* __restrict__ x_expand, Params prm,
                const float* __restrict__ aux, const __nv_bfloat16* __restrict__ dR_out,
@@ -272,8 +281,9 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
                float* __restrict__ dbeta_prev, float* __restrict__ dx_expand, float dx_scale, Grads gr, int M,
                int d) {
   extern __shared__ float sm[];
+  constexpr int TOK = THREADS / TPT, WPT = TPT / 32;
   float* sGradAll = sm + 8 * d;              // [TOK][8][d]: private per token slot -> plain RMW, no atomics
-  float* mailbox = sm + (8 + 8 * TOK) * d;   // [TOK][2][2][24]
+  float* mailbox = sm + (8 + 8 * TOK) * d;   // [TOK][2][WPT][24]
   stage_params(sm, prm, d);
   for (int i = threadIdx.x; i < 8 * TOK * d; i += blockDim.x) sGradAll[i] = 0.f;
   __syncthreads();
@@ -281,13 +291,13 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   const float* sBf = sm + d;
   const float* sLn = sm + 2 * d;
   const float* sA = sm + 3 * d;
-  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
+  const int slot = threadIdx.x / TPT, lt = threadIdx.x % TPT, w2 = lt >> 5, lane = lt & 31;
   float* sGrad = sGradAll + (size_t)slot * 8 * d;
   float* gG = sGrad;
   float* gBf = sGrad + d;
   float* gLn = sGrad + 2 * d;
   float* gA = sGrad + 3 * d;
-  float* mail = mailbox + slot * (2 * 2 * 24);
+  float* mail = mailbox + slot * (2 * WPT * 24);
   int which = 0;
   const int bar_id = 1 + slot;
   const float sqrt_d = sqrtf((float)d);
@@ -303,7 +313,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   int ch[NCH];
   bool act[NCH];
 #pragma unroll
-  for (int k = 0; k < NCH; ++k) { ch[k] = (lt + 64 * k) * 8; act[k] = ch[k] < d; }
+  for (int k = 0; k < NCH; ++k) { ch[k] = (lt + TPT * k) * 8; act[k] = ch[k] < d; }
 
   for (int m = blockIdx.x * TOK + slot; m < M; m += gridDim.x * TOK) {
     const float* a = aux + (size_t)m * AUX;
@@ -380,7 +390,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         for (int e = 0; e < 8; ++e) dmix[0][k][e] = 0.f;
       }
     }
-    slot_sum<2>(lnred, mail, which, w2, lane, bar_id);
+    slot_sum<2, TPT>(lnred, mail, which, w2, lane, bar_id);
     const float m1 = lnred[0] / d, m2 = lnred[1] / d;
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
@@ -411,7 +421,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
           for (int e = 0; e < 8; ++e) acc = fmaf(dmix[t][k][e], R[s][k][e], acc);
         dal[s * T + t] = acc;
       }
-    slot_sum<S * T>(dal, mail, which, w2, lane, bar_id);
+    slot_sum<S * T, TPT>(dal, mail, which, w2, lane, bar_id);
     float dwa[S][T], dwb[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -474,7 +484,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         }
       }
     }
-    slot_sum<S>(udot, mail, which, w2, lane, bar_id);
+    slot_sum<S, TPT>(udot, mail, which, w2, lane, bar_id);
     float dbp[S] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -500,7 +510,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
           *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
     } else {
-      slot_sum<S>(dbp, mail, which, w2, lane, bar_id);
+      slot_sum<S, TPT>(dbp, mail, which, w2, lane, bar_id);
 #pragma unroll
       for (int k = 0; k < NCH; ++k)
         if (act[k]) {
@@ -548,8 +558,10 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   }
 }
 
-inline size_t fwd_smem(int d) { return (size_t)(8 * d + TOK * 2 * 2 * 24) * sizeof(float); }
-inline size_t bwd_smem(int d) { return (size_t)((8 + 8 * TOK) * d + TOK * 2 * 2 * 24) * sizeof(float); }
+inline size_t fwd_smem(int d, int tpt) { return (size_t)(8 * d + (THREADS / tpt) * 2 * (tpt / 32) * 24) * sizeof(float); }
+inline size_t bwd_smem(int d, int tpt) {
+  return (size_t)((8 + 8 * (THREADS / tpt)) * d + (THREADS / tpt) * 2 * (tpt / 32) * 24) * sizeof(float);
+}
 
 }  // namespace hc2
 }  // namespace alm

@@ -298,7 +298,10 @@ def main_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all fwd/dgrad/wgrad launches of a step)",
                      "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"] if pk["tf_sustained"] else None, "traffic": None,
+                     "frac": achieved / pk["tf_sustained"] if pk["tf_sustained"] else None,
+                     # DRAM bytes (read + write) of the 108 GEMM launches of one step from an ncu capture of this
+                     # command (profiles/r01_ncu_gemm_dram_bytes_per_launch_one_step.csv): 13.60 GB + 3.52 GB
+                     "traffic": 17.12e9, "traffic_unit": "bytes per step over all launches of the class",
                      "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
                      "step_algorithmic_tflop": 388e6 * tokens / world / 1e12},
         "kernels": kern,
