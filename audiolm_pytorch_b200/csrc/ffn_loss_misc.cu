@@ -507,6 +507,70 @@ topk_gumbel_kernel(const float* __restrict__ logits, long long ldl, const float*
   }
 }
 
+
+// ---- plain residual + LayerNorm (num_residual_streams == 1: hyper-connections disabled, the reference wraps each
+// branch in Residual(branch), audiolm_pytorch.py:446): r_new = r (+ y);  xn = LN(r_new) * gamma ------------------
+// one warp per row, fp32 residual stream, bf16 branch output y / normed output xn / raw copy `rb` (kv projection input)
+__global__ void resid_ln_fwd_kernel(const float* __restrict__ r, const __nv_bfloat16* __restrict__ y,
+                                    const float* __restrict__ gamma, float* __restrict__ r_new,
+                                    __nv_bfloat16* __restrict__ xn, __nv_bfloat16* __restrict__ rb,
+                                    float* __restrict__ stats, int M, int d) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* rr = r + (size_t)row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    float v = rr[c] + (y ? __bfloat162float(y[(size_t)row * d + c]) : 0.f);
+    if (r_new) r_new[(size_t)row * d + c] = v;
+    s += v;
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = rr[c] + (y ? __bfloat162float(y[(size_t)row * d + c]) : 0.f);
+    q = fmaf(v - mean, v - mean, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+  for (int c = lane; c < d; c += 32) {
+    const float v = rr[c] + (y ? __bfloat162float(y[(size_t)row * d + c]) : 0.f);
+    xn[(size_t)row * d + c] = __float2bfloat16_rn((v - mean) * rstd * gamma[c]);
+    if (rb) rb[(size_t)row * d + c] = __float2bfloat16_rn(v);
+  }
+  if (lane == 0) { stats[(size_t)row * 2] = mean; stats[(size_t)row * 2 + 1] = rstd; }
+}
+
+// dr = dr_out (+) LN-backward(dxn) (+) dextra ; g_gamma += dxn * xhat      (r_new is the forward's output)
+__global__ void resid_ln_bwd_kernel(const float* __restrict__ r_new, const float* __restrict__ gamma,
+                                    const float* __restrict__ stats, const float* __restrict__ dr_out,
+                                    const __nv_bfloat16* __restrict__ dxn, const __nv_bfloat16* __restrict__ dextra,
+                                    float* __restrict__ dr, __nv_bfloat16* __restrict__ dr_bf16,
+                                    float* __restrict__ g_gamma, float out_scale, int M, int d) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float mean = stats[(size_t)row * 2], rstd = stats[(size_t)row * 2 + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float xh = (r_new[(size_t)row * d + c] - mean) * rstd;
+    const float dx = __bfloat162float(dxn[(size_t)row * d + c]);
+    const float gl = dx * gamma[c];
+    atomicAdd(g_gamma + c, dx * xh);
+    s1 += gl;
+    s2 = fmaf(gl, xh, s2);
+  }
+  const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
+  for (int c = lane; c < d; c += 32) {
+    const size_t i = (size_t)row * d + c;
+    const float xh = (r_new[i] - mean) * rstd;
+    const float gl = __bfloat162float(dxn[i]) * gamma[c];
+    float v = rstd * (gl - m1 - xh * m2);
+    if (dr_out) v += dr_out[i];
+    if (dextra) v += __bfloat162float(dextra[i]);
+    v *= out_scale;
+    dr[i] = v;
+    if (dr_bf16) dr_bf16[i] = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace alm
 
 using namespace alm;
@@ -642,6 +706,30 @@ extern "C" int alm_topk_gumbel_sample(const float* logits, int64_t ldl, const fl
   ALM_REQUIRE(V <= SMP_MAXV, ALM_ERR_UNSUPPORTED);
   topk_gumbel_kernel<<<rows, SMP_THREADS, 0, stream>>>(logits, ldl, uniform, ldu, reinterpret_cast<long long*>(ids), V,
                                                        k, 1.f / temperature);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_resid_ln_fwd(const float* r, const void* y, const float* gamma, float* r_new, void* xn, void* rb,
+                                float* stats, int M, int d, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(r && gamma && xn && stats && M > 0 && d > 0, ALM_ERR_ARG);
+  resid_ln_fwd_kernel<<<ceil_div(M * 32, 256), 256, 0, stream>>>(r, (const __nv_bfloat16*)y, gamma, r_new,
+                                                                 (__nv_bfloat16*)xn, (__nv_bfloat16*)rb, stats, M, d);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_resid_ln_bwd(const float* r_new, const float* gamma, const float* stats, const float* dr_out,
+                                const void* dxn, const void* dextra, float* dr, void* dr_bf16, float* g_gamma,
+                                float out_scale, int M, int d, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(r_new && gamma && stats && dxn && dr && g_gamma && M > 0 && d > 0, ALM_ERR_ARG);
+  resid_ln_bwd_kernel<<<ceil_div(M * 32, 256), 256, 0, stream>>>(
+      r_new, gamma, stats, dr_out, (const __nv_bfloat16*)dxn, (const __nv_bfloat16*)dextra, dr,
+      (__nv_bfloat16*)dr_bf16, g_gamma, out_scale, M, d);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;

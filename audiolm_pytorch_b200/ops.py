@@ -362,3 +362,25 @@ def topk_gumbel_sample(logits, uniform, *, k, temperature=1.0):
     _lib.call("alm_topk_gumbel_sample", logits, logits.stride(0), uniform, uniform.stride(0), ids, R, V, int(k),
               float(temperature))
     return ids
+
+
+def resid_ln_fwd(r, y, gamma, *, want_r_new=True, want_raw=False):
+    """plain residual + LayerNorm (num_residual_streams == 1).  r [M,d] fp32, y [M,d] bf16 or None.
+
+    Returns r_new [M,d] fp32 (== r when y is None and want_r_new False), xn bf16, raw bf16 copy (optional), stats."""
+    M, d = r.shape
+    r_new = torch.empty_like(r) if (want_r_new and y is not None) else None
+    xn = torch.empty(M, d, device=r.device, dtype=bf16)
+    raw = torch.empty(M, d, device=r.device, dtype=bf16) if want_raw else None
+    stats = torch.empty(M, 2, device=r.device, dtype=f32)
+    _lib.call("alm_resid_ln_fwd", r, y, gamma, r_new, xn, raw, stats, M, d)
+    return (r_new if r_new is not None else r), xn, raw, stats
+
+
+def resid_ln_bwd(r_new, gamma, stats, dr_out, dxn, dextra, g_gamma, *, out_scale=1.0, want_bf16=True):
+    """dr = out_scale * (dr_out + LN_bwd(dxn) + dextra) as fp32 (and bf16 for the next GEMMs)."""
+    M, d = r_new.shape
+    dr = torch.empty(M, d, device=r_new.device, dtype=f32)
+    dr_b = torch.empty(M, d, device=r_new.device, dtype=bf16) if want_bf16 else None
+    _lib.call("alm_resid_ln_bwd", r_new, gamma, stats, dr_out, dxn, dextra, dr, dr_b, g_gamma, float(out_scale), M, d)
+    return dr, dr_b

@@ -130,6 +130,14 @@ class HyperConnections(nn.Module):
                     alpha_scale=self.dynamic_alpha_scale, beta_scale=self.dynamic_beta_scale)
 
 
+class PlainResidual(nn.Module):
+    """num_residual_streams == 1: the reference wraps the branch in Residual(branch) (audiolm_pytorch.py:446)."""
+
+    def __init__(self, *, dim=None, branch):
+        super().__init__()
+        self.branch = branch
+
+
 HC_KEYS = ("gamma", "dyn_alpha", "dyn_beta", "static_alpha", "static_beta", "alpha_scale", "beta_scale")
 
 
@@ -223,8 +231,8 @@ class Transformer(nn.Module):
         rel_pos_bias = rel_pos_bias and not flash_attn
         if cross_attend or cond_as_self_attn_prefix:
             raise NotImplementedError("text / audio conditioning is outside the accelerated hot path")
-        if num_residual_streams != 4:
-            raise NotImplementedError("hyper-connection kernels are built for num_residual_streams=4")
+        if num_residual_streams not in (1, 4):
+            raise NotImplementedError("residual-stream kernels are built for num_residual_streams in (1, 4)")
         if attn_dropout != 0.0 or ff_dropout != 0.0:
             raise NotImplementedError("dropout > 0 is not built (reference default is 0)")
         if dim % 8 != 0:
@@ -241,13 +249,15 @@ class Transformer(nn.Module):
         self._wants_rel_pos_bias = rel_pos_bias
 
         self.layers = nn.ModuleList([])
+        if num_residual_streams == 1:
+            wrap = lambda branch: PlainResidual(dim=dim, branch=branch)  # noqa: E731
+        else:
+            wrap = lambda branch: HyperConnections(num_residual_streams, dim=dim, branch=branch)  # noqa: E731
         for _ in range(depth):
             self.layers.append(nn.ModuleList([
-                HyperConnections(num_residual_streams, dim=dim,
-                                 branch=Attention(dim=dim, heads=heads, dropout=attn_dropout, flash=flash_attn,
-                                                  causal=True, **kwargs)),
+                wrap(Attention(dim=dim, heads=heads, dropout=attn_dropout, flash=flash_attn, causal=True, **kwargs)),
                 None,
-                HyperConnections(num_residual_streams, dim=dim, branch=FeedForward(dim=dim, dropout=ff_dropout)),
+                wrap(FeedForward(dim=dim, dropout=ff_dropout)),
             ]))
         self.norm = LayerNorm(dim)
         self._packed = _PackedWeights()
@@ -258,6 +268,14 @@ class Transformer(nn.Module):
 
     # ---- parameter plumbing ------------------------------------------------------------------
     def _param_list(self):
+        if self.num_residual_streams == 1:
+            ps = []
+            for attn_w, _, ff_w in self.layers:
+                a, f = attn_w.branch, ff_w.branch
+                ps += [a.norm.gamma, a.to_q.weight, a.to_kv.weight, a.to_out[0].weight, getattr(f, "0").gamma,
+                       getattr(f, "1").weight, getattr(f, "3").gamma, getattr(f, "5").weight]
+            ps.append(self.norm.gamma)
+            return ps
         ps = []
         for attn_hc, _, ff_hc in self.layers:
             a, f = attn_hc.branch, ff_hc.branch
@@ -304,6 +322,8 @@ class Transformer(nn.Module):
         return out, kv
 
     def _run_forward(self, x, mask, save):
+        if self.num_residual_streams == 1:
+            return self._run_forward_plain(x, mask, save)
         b, n, d = x.shape
         M = b * n
         H = self.heads
@@ -354,6 +374,8 @@ class Transformer(nn.Module):
 
     # ---- backward ------------------------------------------------------------------------------
     def _run_backward(self, S, dout):
+        if self.num_residual_streams == 1:
+            return self._run_backward_plain(S, dout)
         b, n, d = S["shape"]
         M = b * n
         H = self.heads
@@ -429,12 +451,123 @@ class Transformer(nn.Module):
                                     M=M, d=d)
         return dx.view(b, n, d).to(S["x_dtype"]), grads
 
+
+    # ---- num_residual_streams == 1: plain residual stream (fp32) ---------------------------------
+    def _attn_branch_fwd(self, i, xn, raw, b, n, mask_u8, v_first, cache=None):
+        """q/kv projections, value residual, (optional KV cache), attention, output projection."""
+        H = self.heads
+        W = self._weights(i)
+        M = b * n
+        q = ops.gemm(xn, W["wq"])
+        kv = ops.gemm(raw, W["wkv"])
+        if self.add_value_residual and v_first is not None:
+            ops.axpby(kv[:, 64:], 0.5, v_first, 0.5, out=kv[:, 64:])
+        elif self.add_value_residual:
+            v_first = kv[:, 64:].clone()
+        k3 = kv[:, :64].unflatten(0, (b, n))
+        v3 = kv[:, 64:].unflatten(0, (b, n))
+        if cache is not None:
+            k3 = torch.cat((cache[0].to(bf16), k3), dim=1).contiguous()
+            v3 = torch.cat((cache[1].to(bf16), v3), dim=1).contiguous()
+        o, lse = ops.mqa_attn_fwd(q.view(b, n, H * 64), k3, v3, heads=H, key_mask=mask_u8, causal=True)
+        o2 = o.view(M, H * 64)
+        Y = ops.gemm(o2, W["wo"])
+        return q, kv, o2, lse, Y, v_first, torch.stack((k3, v3))
+
+    def _run_forward_plain(self, x, mask, save, kv_cache=None):
+        b, n, d = x.shape
+        M = b * n
+        r = x.detach().reshape(M, d).to(f32).contiguous()
+        x2 = r
+        mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        L, kvs = [], []
+        a0 = self.layers[0][0].branch
+        r, xn, raw, st = ops.resid_ln_fwd(r, None, a0.norm.gamma, want_raw=True)
+        v_first = None
+        for i, (attn_w, _, ff_w) in enumerate(self.layers):
+            a, f = attn_w.branch, ff_w.branch
+            W = self._weights(i)
+            inner, ip = f.inner, _pad8(f.inner)
+            q, kv, o2, lse, Y, v_first, kv_t = self._attn_branch_fwd(
+                i, xn, raw, b, n, mask_u8, v_first, None if kv_cache is None else kv_cache[i])
+            kvs.append(kv_t)
+            r_f, xn_f, _, st_f = ops.resid_ln_fwd(r, Y, getattr(f, "0").gamma)
+            h = ops.gemm(xn_f, W["w1"])
+            gn, stg = ops.geglu_ln_fwd(h, getattr(f, "3").gamma, inner=inner, inner_pad=ip)
+            Y2 = ops.gemm(gn, W["w2"])
+            L.append(dict(r_a=r, st_a=st, xn_a=xn, raw_a=raw, q=q, kv=kv, o=o2, lse=lse, r_f=r_f, st_f=st_f, xn_f=xn_f,
+                          h=h, gn=gn, stg=stg))
+            if i + 1 < self.depth:
+                nxt = self.layers[i + 1][0].branch
+                r, xn, raw, st = ops.resid_ln_fwd(r_f, Y2, nxt.norm.gamma, want_raw=True)
+        r_last, out, _, st_last = ops.resid_ln_fwd(r_f, Y2, self.norm.gamma)
+        saved = dict(kv=torch.stack(kvs))
+        if save:
+            saved.update(L=L, mask=mask_u8, r_last=r_last, st_last=st_last, shape=(b, n, d), x_dtype=x.dtype)
+        return out.view(b, n, d), saved
+
+    def _run_backward_plain(self, S, dout):
+        b, n, d = S["shape"]
+        M = b * n
+        H = self.heads
+        dev = dout.device
+        L = S["L"]
+        dout = dout.reshape(M, d).to(bf16).contiguous()
+        params = self._param_list()
+        grads = [torch.zeros_like(p, dtype=f32) for p in params]
+        dr, dr_b = ops.resid_ln_bwd(S["r_last"], self.norm.gamma, S["st_last"], None, dout, None, grads[-1])
+        dv_first = None
+        for i in reversed(range(self.depth)):
+            attn_w, _, ff_w = self.layers[i]
+            a, f = attn_w.branch, ff_w.branch
+            inner, ip = f.inner, _pad8(f.inner)
+            W = self._weights(i)
+            rec = L[i]
+            g_ln_a, g_wq, g_wkv, g_wo, g_ln_f, g_w1, g_ln2, g_w2 = grads[i * 8:(i + 1) * 8]
+            # feed-forward branch (its output gradient is the residual-stream gradient)
+            dgn = ops.gemm(dr_b, W["w2"], b_mn=True)
+            _wgrad_cols(dr_b, rec["gn"], g_w2, inner)
+            dh = ops.geglu_ln_bwd(rec["h"], getattr(f, "3").gamma, rec["stg"], dgn, g_ln2, inner=inner, inner_pad=ip)
+            dxn_f = ops.gemm(dh, W["w1"], b_mn=True)
+            wgrad(dh[:, :inner], rec["xn_f"], g_w1[:inner])
+            wgrad(dh[:, ip:ip + inner], rec["xn_f"], g_w1[inner:])
+            dr, dr_b = ops.resid_ln_bwd(rec["r_f"], getattr(f, "0").gamma, rec["st_f"], dr, dxn_f, None, g_ln_f)
+            # attention branch
+            dO = ops.gemm(dr_b, W["wo"], b_mn=True)
+            wgrad(dr_b, rec["o"], g_wo)
+            kv = rec["kv"]
+            k3 = kv[:, :64].unflatten(0, (b, n))
+            v3 = kv[:, 64:].unflatten(0, (b, n))
+            dq, dk, dv = ops.mqa_attn_bwd(rec["q"].view(b, n, H * 64), k3, v3, rec["o"].view(b, n, H * 64),
+                                          dO.view(b, n, H * 64), rec["lse"], heads=H, key_mask=S["mask"], causal=True)
+            dkv = torch.empty(M, 128, device=dev, dtype=bf16)
+            ops.axpby(dk.view(M, 64), 1.0, None, 0.0, out=dkv[:, :64])
+            dv2 = dv.view(M, 64)
+            if self.add_value_residual and i > 0:
+                ops.axpby(dv2, 0.5, None, 0.0, out=dkv[:, 64:])
+                dv_first = ops.axpby(dv2, 0.5, dv_first, 1.0) if dv_first is not None else ops.axpby(dv2, 0.5, None, 0.0)
+            elif self.add_value_residual and dv_first is not None:
+                ops.axpby(dv2, 1.0, dv_first, 1.0, out=dkv[:, 64:])
+            else:
+                ops.axpby(dv2, 1.0, None, 0.0, out=dkv[:, 64:])
+            dq2 = dq.view(M, H * 64)
+            dxn_a = ops.gemm(dq2, W["wq"], b_mn=True)
+            dbin_a = ops.gemm(dkv, W["wkv"], b_mn=True)
+            wgrad(dq2, rec["xn_a"], g_wq)
+            wgrad(dkv, rec["raw_a"], g_wkv)
+            dr, dr_b = ops.resid_ln_bwd(rec["r_a"], a.norm.gamma, rec["st_a"], dr, dxn_a, dbin_a, g_ln_a,
+                                        out_scale=self.grad_shrink_alpha if i == 0 else 1.0)
+        return dr.view(b, n, d).to(S["x_dtype"]), grads
+
     # ---- incremental (KV-cache) inference ------------------------------------------------------
     @torch.no_grad()
     def _forward_cached(self, x, mask, kv_cache):
         """x is the FULL sequence; only x[:, cache_len:] is processed (audiolm_pytorch.py:489-496)."""
         cache_len = kv_cache.shape[-2]
         x = x[:, cache_len:]
+        if self.num_residual_streams == 1:
+            out, saved = self._run_forward_plain(x, mask, save=False, kv_cache=kv_cache)
+            return out, saved["kv"]
         b, n, d = x.shape
         M = b * n
         H = self.heads

@@ -115,6 +115,15 @@ int alm_hc_post_bwd(const void* R_in, const void* Y, const float* beta_prev, con
                     const float* stats, const void* dout, void* dR_in, void* dY, float* dbeta_prev,
                     float* g_ln_gamma, int M, int d, int streams, alm_stream_t stream);
 
+/* ---- plain residual + pre-LayerNorm (num_residual_streams == 1: Residual(branch), audiolm_pytorch.py:446) ------ */
+/* r_new = r (+ y);  xn = LN(r_new) * gamma;  rb = bf16 copy of r_new (k/v projection input).  fp32 residual stream. */
+int alm_resid_ln_fwd(const float* r, const void* y, const float* gamma, float* r_new, void* xn, void* rb, float* stats,
+                     int M, int d, alm_stream_t stream);
+/* dr = out_scale * (dr_out + LayerNorm-backward(dxn) + dextra);  g_gamma += dxn * xhat */
+int alm_resid_ln_bwd(const float* r_new, const float* gamma, const float* stats, const float* dr_out, const void* dxn,
+                     const void* dextra, float* dr, void* dr_bf16, float* g_gamma, float out_scale, int M, int d,
+                     alm_stream_t stream);
+
 /* ---- FeedForward inner part: GEGLU + LayerNorm(inner) (audiolm_pytorch.py:246-258) -------------- */
 /* h [M, ldh] bf16 holds a = h[:, 0:inner] and gate = h[:, gate_off:gate_off+inner];
  * gn[M, ldg] = LN(gelu(gate) * a) * gamma, columns [inner, inner_pad) are written as zeros. */

@@ -123,6 +123,30 @@ def golden_semantic(ref):
                     cache12=cache, logits_inc=l_inc, loss=loss.detach(), grads=grads), GOLDEN / "semantic.pt")
 
 
+def golden_semantic_plain(ref):
+    """num_residual_streams=1 (hyper-connections disabled -> plain Residual wrappers, audiolm_pytorch.py:446)."""
+    torch.manual_seed(22)
+    kw = dict(num_semantic_tokens=50, dim=64, depth=2, heads=2, flash_attn=True, num_residual_streams=1)
+    m = ref.lm.SemanticTransformer(**kw).eval()
+    perturb(m, 5)
+    ids = torch.randint(0, 50, (2, 19))
+    mask = ot.fcm_mask((2, 19), 0.15, torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        logits = m(ids=ids)
+        logits_masked = m(ids=ids, self_attn_mask=mask)
+    st = clone_state(m)
+    print("semantic (1 residual stream):")
+    hk = dict(heads=2, depth=2, num_streams=1)
+    check("logits", ot.semantic_forward(st, ids, **hk)[0], logits)
+    check("logits masked", ot.semantic_forward(st, ids, self_attn_mask=mask, **hk)[0], logits_masked)
+    w = ref.lm.SemanticTransformerWrapper(transformer=m, unique_consecutive=False, mask_prob=0.0).train()
+    loss = w(semantic_token_ids=ids, return_loss=True)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    torch.save(dict(kwargs=kw, state=st, ids=ids, mask=mask, logits=logits, logits_masked=logits_masked,
+                    loss=loss.detach(), grads=grads), GOLDEN / "semantic_plain.pt")
+
+
 def golden_coarse(ref):
     torch.manual_seed(31)
     kw = dict(num_semantic_tokens=50, codebook_size=64, num_coarse_quantizers=3, dim=64, depth=2, heads=2,
@@ -267,6 +291,7 @@ def main():
         warnings.simplefilter("ignore")
         golden_attend(ref)
         golden_semantic(ref)
+        golden_semantic_plain(ref)
         golden_coarse(ref)
         golden_fine(ref)
         golden_sampling(ref)

@@ -15,7 +15,8 @@ def load(name):
 
 
 @pytest.mark.parametrize("fixture,cls_name", [("semantic.pt", "SemanticTransformer"), ("coarse.pt", "CoarseTransformer"),
-                                              ("fine.pt", "FineTransformer")])
+                                              ("fine.pt", "FineTransformer"),
+                                              ("semantic_plain.pt", "SemanticTransformer")])
 def test_state_dict_keys_match_reference(fixture, cls_name):
     from audiolm_pytorch_b200 import audiolm
 
@@ -35,7 +36,7 @@ def test_c_abi_exports_every_declared_symbol():
         build.build()
     lib = ctypes.CDLL(str(lib_path))
     header = (ROOT / "include" / "alm_b200.h").read_text()
-    names = set(re.findall(r"\b(alm_[a-z0-9_]+)\s*\(", header))
+    names = set(re.findall(r"\b(alm_[A-Za-z0-9_]+)\s*\(", header))
     assert len(names) >= 15
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/alm_b200.h but not exported"

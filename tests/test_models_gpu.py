@@ -263,3 +263,24 @@ def test_grads_vs_oracle_autograd_more_tokens():
         print(f"  grad err {e:.4f} (tol {tol}) {k}  ref={golden[k].flatten()[:4].tolist()} got={named[k].grad.flatten()[:4].tolist()}")
     bad = {k: v for k, v in errs.items() if v[0] >= v[1]}
     assert not bad, bad
+
+
+def test_single_residual_stream_path():
+    """num_residual_streams=1 (plain Residual wrappers): logits, loss and every gradient vs the reference golden."""
+    from audiolm_pytorch_b200.audiolm import SemanticTransformer, SemanticTransformerWrapper
+
+    g = load("semantic_plain.pt")
+    m = build(SemanticTransformer, g).eval()
+    ids = g["ids"].to(DEV)
+    with torch.no_grad():
+        logits = m(ids=ids)
+        masked = m(ids=ids, self_attn_mask=g["mask"].to(DEV))
+        l12, cache = m(ids=ids[:, :12], return_kv_cache=True)
+        inc, _ = m(ids=ids, kv_cache=cache, return_kv_cache=True)
+    assert rms_rel(logits, g["logits"]) < 1e-2 and rms_rel(masked, g["logits_masked"]) < 1e-2
+    assert rms_rel(inc, logits[:, 13:]) < 1.5e-2
+    w = SemanticTransformerWrapper(transformer=m, unique_consecutive=False, mask_prob=0.0).train()
+    loss = w(semantic_token_ids=ids, return_loss=True)
+    assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
+    loss.backward()
+    check_grads(dict(m.named_parameters()), g["grads"])

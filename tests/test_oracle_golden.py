@@ -42,6 +42,13 @@ def test_semantic():
     assert close(inc, g["logits"][:, 13:], 1e-3)  # KV-cache decode == full forward
 
 
+def test_semantic_single_residual_stream():
+    g = load("semantic_plain.pt")
+    hk = dict(heads=2, depth=2, num_streams=1)
+    assert close(ot.semantic_forward(g["state"], g["ids"], **hk)[0], g["logits"])
+    assert close(ot.semantic_forward(g["state"], g["ids"], self_attn_mask=g["mask"], **hk)[0], g["logits_masked"])
+
+
 def test_semantic_grads():
     g = load("semantic.pt")
     st = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state"].items()}
