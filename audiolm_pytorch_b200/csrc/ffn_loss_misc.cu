@@ -59,6 +59,16 @@ geglu_ln_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
                     float* __restrict__ stats, int M, int inner, int inner_pad) {
   __shared__ float buf[2 * 8];
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    if (m + (int)gridDim.x < M && (threadIdx.x & 7) == 0) {  // L2 prefetch of this CTA's next row
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+        if (c0 < inner_pad) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + c0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + gate_off + c0));
+        }
+      }
+    }
     float g[NCH][8];
     float s1[1] = {0.f};
 #pragma unroll
@@ -119,6 +129,17 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
 #pragma unroll
     for (int e = 0; e < 8; ++e) gacc[k][e] = 0.f;
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    if (m + (int)gridDim.x < M && (threadIdx.x & 7) == 0) {  // L2 prefetch of this CTA's next row
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+        if (c0 < inner_pad) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + c0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + gate_off + c0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dgn + (size_t)(m + gridDim.x) * ldg + c0));
+        }
+      }
+    }
     const float mean = stats[(size_t)m * 2], rstd = stats[(size_t)m * 2 + 1];
     // one erf per element: ge = gelu(gate) is kept; Phi(gate) = ge / gate is recovered from it in the second phase
     float a[NCH][8], gt[NCH][8], gl[NCH][8], ge[NCH][8];

@@ -171,6 +171,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     int iter = 0;
+    uint32_t store_seq = 0;  // running count of staged chunks: picks the staging buffer (also across tiles)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
       int b, s, mb, nb;
       decode(t, b, s, mb, nb);
@@ -188,18 +189,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool leader = (warp == 4 && lane == 0);
 #pragma unroll 1
         for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
-          uint8_t* stage_c = smem_c + (cc & 1) * (GEMM_BLOCK_M * 128);
-          if (leader) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+          if (n0 + cc * 64 >= p.N) break;  // CTA-uniform: the remaining chunks lie beyond N (nothing staged/stored)
+          // staging buffers alternate per ISSUED store (also across tiles), so "at most one bulk group still
+          // reading" below always means the other buffer
+          uint8_t* stage_c = smem_c + (store_seq & 1u) * (GEMM_BLOCK_M * 128);
+          ++store_seq;
+          if (leader) tma_store_wait_read<1>();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(taddr + cc * 64, r0);
           tmem_ld_32x32b_x32(taddr + cc * 64 + 32, r1);
           tmem_ld_wait();
-          if (cc == BLOCK_N / 64 - 1) {
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
-          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 o;
@@ -216,11 +216,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (leader && n0 + cc * 64 < p.N) {
+          if (leader) {
             tma_store_3d(&tmC, stage_c, n0 + cc * 64, mb * GEMM_BLOCK_M, b);
             tma_store_commit();
           }
         }
+        // every TMEM read of this accumulator has completed (tcgen05.wait::ld above): hand it back to the MMA warp
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
         continue;
       }
 #pragma unroll 1

@@ -56,6 +56,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(pk(f[0], f[1]), pk(f[2], f[3]), pk(f[4], f[5]), pk(f[6], f[7]));
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ void lds4(const float* p, float* f) {
   const float4 v = *reinterpret_cast<const float4*>(p);
   f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
@@ -121,6 +125,23 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   for (int k = 0; k < NCH; ++k) { ch[k] = (lt + TPT * k) * 8; act[k] = ch[k] < d; }
 
   for (int m = blockIdx.x * TOK + slot; m < M; m += gridDim.x * TOK) {
+    {  // pull the next token of this slot towards L2 while this one is processed (one lane per 128-B line)
+      const int mn = m + gridDim.x * TOK;
+      if (mn < M && (lt & 7) == 0) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          if (act[k]) {
+            if (x_expand != nullptr) {
+              prefetch_l2(x_expand + (size_t)mn * d + ch[k]);
+              prefetch_l2(x_expand + (size_t)mn * d + ch[k] + 32);
+            } else {
+              prefetch_l2(Y + (size_t)mn * d + ch[k]);
+#pragma unroll
+              for (int s = 0; s < S; ++s) prefetch_l2(R_in + ((size_t)mn * S + s) * d + ch[k]);
+            }
+          }
+      }
+    }
     float R[S][NCH][8];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -316,6 +337,27 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   for (int k = 0; k < NCH; ++k) { ch[k] = (lt + TPT * k) * 8; act[k] = ch[k] < d; }
 
   for (int m = blockIdx.x * TOK + slot; m < M; m += gridDim.x * TOK) {
+    {  // L2 prefetch of the next token's rows (the kernel is latency-bound at 8 warps / SM)
+      const int mn = m + gridDim.x * TOK;
+      if (mn < M && (lt & 7) == 0) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          if (act[k]) {
+            if (x_expand != nullptr) {
+              prefetch_l2(x_expand + (size_t)mn * d + ch[k]);
+              prefetch_l2(x_expand + (size_t)mn * d + ch[k] + 32);
+            } else {
+              prefetch_l2(Y + (size_t)mn * d + ch[k]);
+#pragma unroll
+              for (int s = 0; s < S; ++s) prefetch_l2(R_in + ((size_t)mn * S + s) * d + ch[k]);
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) prefetch_l2(dR_out + ((size_t)mn * S + s) * d + ch[k]);
+            prefetch_l2(dxn + (size_t)mn * d + ch[k]);
+            if (dbin_extra != nullptr) prefetch_l2(dbin_extra + (size_t)mn * d + ch[k]);
+          }
+      }
+    }
     const float* a = aux + (size_t)m * AUX;
     float ta[S][T], tb[S], inv[S], alpha[S][T], bp[S], dbe[S];
 #pragma unroll

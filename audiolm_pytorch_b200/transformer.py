@@ -221,6 +221,25 @@ class _StackFn(torch.autograd.Function):
         return (None, dx, None, *grads)
 
 
+def _grad_targets(params):
+    """Where the backward accumulates parameter gradients.
+
+    If every parameter already owns a contiguous fp32 `.grad` (e.g. views of parallel.FlatGradBucket), the kernels
+    accumulate straight into it (wgrad GEMMs in accumulate mode, atomics for the small tensors) and autograd is
+    handed `None` — no temporaries, no 130 `grad += tmp` launches.  Otherwise fresh zero buffers (one flat
+    allocation, one memset) are returned to autograd."""
+    direct = all(p.grad is not None and p.grad.dtype == f32 and p.grad.is_contiguous() for p in params)
+    if direct:
+        return [p.grad for p in params], [None] * len(params)
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, device=params[0].device, dtype=f32)
+    out, off = [], 0
+    for p in params:
+        out.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+    return out, out
+
+
 class Transformer(nn.Module):
     """audiolm_pytorch.py:410-560 (self-attention stack with hyper-connections and value residual)."""
 
@@ -383,7 +402,7 @@ class Transformer(nn.Module):
         L = S["L"]
         dout = dout.reshape(M, d).to(bf16).contiguous()
         params = self._param_list()
-        grads = [torch.zeros_like(p, dtype=f32) for p in params]
+        grads, returned = _grad_targets(params)
         PL = self.PER_LAYER
         nk = len(HC_KEYS)
 
@@ -449,7 +468,7 @@ class Transformer(nn.Module):
                 dx = ops.hc_pre_bwd(attn_hc.kernel_params(), a.norm.gamma, a_hc, g_ln_a, rec["aux_a"], dR_a, dxn_a,
                                     dbeta_a, dbin_extra=dbin_a, x_expand=S["x2"], dx_scale=self.grad_shrink_alpha,
                                     M=M, d=d)
-        return dx.view(b, n, d).to(S["x_dtype"]), grads
+        return dx.view(b, n, d).to(S["x_dtype"]), returned
 
 
     # ---- num_residual_streams == 1: plain residual stream (fp32) ---------------------------------
@@ -514,7 +533,7 @@ class Transformer(nn.Module):
         L = S["L"]
         dout = dout.reshape(M, d).to(bf16).contiguous()
         params = self._param_list()
-        grads = [torch.zeros_like(p, dtype=f32) for p in params]
+        grads, returned = _grad_targets(params)
         dr, dr_b = ops.resid_ln_bwd(S["r_last"], self.norm.gamma, S["st_last"], None, dout, None, grads[-1])
         dv_first = None
         for i in reversed(range(self.depth)):
@@ -557,7 +576,7 @@ class Transformer(nn.Module):
             wgrad(dkv, rec["raw_a"], g_wkv)
             dr, dr_b = ops.resid_ln_bwd(rec["r_a"], a.norm.gamma, rec["st_a"], dr, dxn_a, dbin_a, g_ln_a,
                                         out_scale=self.grad_shrink_alpha if i == 0 else 1.0)
-        return dr.view(b, n, d).to(S["x_dtype"]), grads
+        return dr.view(b, n, d).to(S["x_dtype"]), returned
 
     # ---- incremental (KV-cache) inference ------------------------------------------------------
     @torch.no_grad()

@@ -133,3 +133,47 @@ def test_c1_codec_properties():
         recon = ss(wave, return_recons_only=True)
         assert recon.shape == (4, 1, 48000)
         assert torch.allclose(ss.decode_from_codebook_indices(idx), recon, atol=1e-5)
+
+
+@pytest.mark.parametrize("which", ["C2", "C3", "C4"])
+def test_full_size_logits_vs_cpu_oracle(which):
+    """BASELINE.json configs at full model size and sequence length (batch 1): CUDA logits vs the CPU oracle.
+    bf16 activations / fp32 accumulation vs fp32: RMS-relative error < 1e-2 (north_star tolerance)."""
+    from audiolm_pytorch_b200 import audiolm
+    from oracle import transformer as ot
+
+    torch.manual_seed({"C2": 2, "C3": 3, "C4": 4}[which])
+    kw = dict(dim=1024, depth=6, heads=8, flash_attn=True)
+    if which == "C2":
+        m = audiolm.SemanticTransformer(num_semantic_tokens=500, **kw)
+    elif which == "C3":
+        m = audiolm.CoarseTransformer(num_semantic_tokens=500, codebook_size=1024, num_coarse_quantizers=3, **kw)
+    else:
+        m = audiolm.FineTransformer(num_coarse_quantizers=3, num_fine_quantizers=5, codebook_size=1024, **kw)
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "dynamic_alpha_fn" in n_ or "dynamic_beta_fn" in n_:
+                p.normal_(0, 0.02)
+            if "logit_weights" in n_:
+                p.mul_(0.05)
+    st = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    hk = dict(heads=8, depth=6)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    with torch.no_grad():
+        if which == "C2":
+            ids = torch.randint(0, 500, (1, 1023))
+            ref = [ot.semantic_forward(st, ids, **hk)[0]]
+            got = [m.to(DEV).eval()(ids=ids.to(DEV))]
+        elif which == "C3":
+            sem, co = torch.randint(0, 500, (1, 372)), torch.randint(0, 1024, (1, 1674))
+            ref = list(ot.coarse_forward(st, sem, co, codebook_size=1024, num_coarse_quantizers=3, **hk)[0])
+            got = list(m.to(DEV).eval()(semantic_token_ids=sem.to(DEV), coarse_token_ids=co.to(DEV)))
+        else:
+            co, fi = torch.randint(0, 1024, (1, 768)), torch.randint(0, 1024, (1, 1278))
+            ref = list(ot.fine_forward(st, co, fi, codebook_size=1024, num_coarse_quantizers=3, num_fine_quantizers=5,
+                                       **hk)[0])
+            got = list(m.to(DEV).eval()(coarse_token_ids=co.to(DEV), fine_token_ids=fi.to(DEV)))
+    for r, g_ in zip(ref, got):
+        assert r.shape == g_.shape
+        e = ((g_.float().cpu() - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()).item()
+        assert e < 1e-2, (which, e)
