@@ -129,20 +129,30 @@ def run_cpu(steps, warmup, batch=1):
     return batch * SEQ * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+WORKLOAD = ("C3 CoarseTransformer d1024 L6 h8 4-stream hyper-connections, flash path, "
+            "batch 16/GPU x seq 2048, fwd + CE + bwd")
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints went to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     tps, ms, cores = run_cpu(args.steps, args.warmup)
     sample = f"batch 1 x {SEQ} tokens per step, fp32, oracle port of the reference path (torch CPU, {cores} threads)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3 CoarseTransformer d1024 L6 h8 seq2048 fwd+bwd (CPU: batch 1 per step)"},
+        "config": {"workload": WORKLOAD + " (CPU arm: bounded sample, see cpu_baseline.sample)", "seq_len": SEQ,
+                   "global_batch": BATCH * args.gpus, "parallelism": f"dp{args.gpus}"},
         "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -288,8 +298,7 @@ def main_ours(args):
         "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "C3 CoarseTransformer d1024 L6 h8 4-stream hyper-connections, flash path, "
-                               "batch 16/GPU x seq 2048, fwd + CE + bwd" + (" + grad all-reduce" if world > 1 else ""),
+        "config": {"workload": WORKLOAD + (" + grad all-reduce" if world > 1 else ""),
                    "global_batch": world * BATCH, "seq_len": SEQ, "parallelism": f"dp{world}", "params": n_params,
                    "l2": "working set (~9 GB of saved activations per step) far exceeds the 126 MB L2"},
         "e2e": {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s",
@@ -318,7 +327,7 @@ def main_ours(args):
                                     "sample": f"1 warm-up + 1 timed fwd+bwd of batch 1 x {SEQ} tokens, fp32 oracle port"}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -331,6 +340,10 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline leg")
     a = ap.parse_args()
+    # NCCL / torch may print banners ("NCCL version ...") on fd 1: keep stdout for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         main_reference(a)
     else:
