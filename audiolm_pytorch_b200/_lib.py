@@ -22,9 +22,11 @@ F = C.c_float
 # name -> argtypes (stream is always last and always a void*)
 SIGNATURES: dict[str, list] = {
     "alm_gemm_bf16": [P, I, L, L, P, I, L, L, P, I, L, L, I, I, I, I, F, P, I, I, P],
-    "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, L, I, I, I, I, I, F, P],
-    "alm_mqa_attn_bwd": [P, L, P, L, L, P, L, L, P, L, P, P, P, I, P, L, P, L, P, L, I, I, I, I, I, F, P],
+    "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, L, P, L, L, I, I, I, I, I, F, P],
+    "alm_mqa_attn_bwd": [P, L, P, L, L, P, L, L, P, L, P, P, P, I, P, L, P, L, P, L, P, P, L, L, I, I, I, I, I, F, P],
     "alm_attn_delta": [P, L, P, L, P, L, I, I, I, P],
+    "alm_bias_gather_fwd": [P, P, P, P, I, I, I, L, P],
+    "alm_bias_gather_bwd": [P, P, P, P, I, I, I, L, P],
     "alm_hc_pre_fwd": [P] * 12 + [P, P, P, P, P, I, I, I, P],
     "alm_hc_pre_bwd": [P] * 12 + [P, P, P, P, P, P, P, P, P, F] + [P] * 8 + [I, I, I, P],
     "alm_hc_post_fwd": [P, P, P, P, P, P, I, I, I, P],

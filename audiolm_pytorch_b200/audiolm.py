@@ -1,9 +1,10 @@
 """The three AudioLM transformers, their training / sampling wrappers and the AudioLM orchestrator.
 
 Drop-in surface of /root/reference/audiolm_pytorch/audiolm_pytorch.py:564-2254 (same class names, keyword
-arguments, return conventions and state_dict keys) for the configuration the hot path covers:
-`flash_attn=True` (no relative-position bias), no text / audio conditioning.  Token bookkeeping (ids,
-masks, sampling loops) is host-side torch; every FLOP of the transformer runs in libalm_b200.
+arguments, return conventions and state_dict keys) for the configuration the hot path covers: both the
+`flash_attn=True` path and the `flash_attn=False` path with its relative-position attention bias
+(rel_pos.py), no text / audio conditioning.  Token bookkeeping (ids, masks, sampling loops) is host-side
+torch; the transformer stack, heads, loss and sampler run in libalm_b200.
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ from torch import nn
 
 from .heads import (HeadCache, cross_entropy, generate_mask_with_prob, gumbel_sample, mask_out_after_eos_id, top_k)
 from . import ops
+from .rel_pos import gather_bias, mlp_table
 from .transformer import Transformer, default, exists
 
 __version__ = "2.4.0"  # checkpoint 'version' field of the reference this surface mirrors
@@ -142,6 +144,7 @@ class CoarseTransformer(_TokenTransformer):
         self.transformer = Transformer(dim=dim, depth=depth, heads=heads, attn_dropout=attn_dropout,
                                        ff_dropout=ff_dropout, grad_shrink_alpha=grad_shrink_alpha,
                                        rel_pos_bias=rel, flash_attn=flash_attn, **kwargs)
+        self._bias_idx = {}
         self.codebook_size = codebook_size
         self.num_coarse_quantizers = num_coarse_quantizers
         self.to_semantic_logits = nn.Linear(dim, num_semantic_tokens + 1) if project_semantic_logits else None
@@ -154,6 +157,16 @@ class CoarseTransformer(_TokenTransformer):
         logits, (new_kv, new_emb) = self.forward(*args, cond_drop_prob=0.0, return_cache=True, kv_cache=kv,
                                                  embed_cache=emb, **kwargs)
         return (logits, (new_kv[None], new_emb[None])) if return_kv_cache else logits
+
+    def _cross_index(self, n, n_sem, dev):
+        """table row per (i, j) as RelativePositionBias.index, -1 where exactly one of i, j is semantic."""
+        key = (n, n_sem, str(dev))
+        if self._bias_idx.get("key") != key:
+            idx = self.transformer.rel_pos_bias.index(n, n).clone()
+            is_sem = torch.arange(n, device=dev) < n_sem
+            idx[is_sem[:, None] ^ is_sem[None, :]] = -1
+            self._bias_idx = dict(key=key, idx=idx)
+        return self._bias_idx["idx"]
 
     def forward(self, *, semantic_token_ids, coarse_token_ids, self_attn_mask=None, text=None, text_embeds=None,
                 cond_drop_prob=None, return_only_coarse_logits=False, return_cache=False, kv_cache=None,
@@ -173,8 +186,15 @@ class CoarseTransformer(_TokenTransformer):
         S = sem.shape[1]
         tokens = torch.cat((self.semantic_start_token.expand(b, 1, -1), sem,
                             self.coarse_start_token.expand(b, 1, -1), coarse), dim=1)
-        tokens, new_kv = self.transformer(tokens, self_attn_mask=self_attn_mask, kv_cache=kv_cache,
-                                          return_kv_cache=True)
+        # relative position bias, except between the semantic and the coarse segment where one learned scalar
+        # per head is used so cross attention is not dominated by relative positions (:920-936)
+        attn_bias = None
+        rp = self.transformer.rel_pos_bias
+        if exists(rp):
+            seq_len = tokens.shape[-2]
+            attn_bias = gather_bias(rp.table(seq_len), self.cross_attn_bias, self._cross_index(seq_len, S + 1, dev))
+        tokens, new_kv = self.transformer(tokens, self_attn_mask=self_attn_mask, attn_bias=attn_bias,
+                                          kv_cache=kv_cache, return_kv_cache=True)
         if exists(embed_cache):
             tokens = torch.cat((embed_cache.to(tokens.dtype), tokens), dim=-2)
         new_embed_cache = tokens
@@ -214,10 +234,14 @@ class FineTransformer(_TokenTransformer):
         self.transformer = Transformer(dim=dim, depth=depth, heads=heads, attn_dropout=attn_dropout,
                                        ff_dropout=ff_dropout, rel_pos_bias=False,
                                        grad_shrink_alpha=grad_shrink_alpha, flash_attn=flash_attn, **kwargs)
-        if rel:
-            raise NotImplementedError("the 2-D relative position bias MLP (flash_attn=False) is not built yet")
-        self.null_pos_bias = None
-        self.pos_bias_mlp = None
+        # 2-D (frame distance, quantizer distance) bias MLP + the start tokens' own bias (:1059-1071)
+        self.null_pos_bias = nn.Parameter(torch.randn(heads, 1, 1)) if rel else None
+        mlp_dim = dim // 2
+        self.pos_bias_mlp = nn.Sequential(
+            nn.Linear(2, mlp_dim), nn.SiLU(), nn.Linear(mlp_dim, mlp_dim), nn.SiLU(), nn.Linear(mlp_dim, heads)
+        ) if rel else None
+        self._bias_cache = HeadCache()
+        self._bias_idx = {}
         self.coarse_logit_weights = (nn.Parameter(torch.randn(num_coarse_quantizers, codebook_size, dim))
                                      if project_coarse_logits else None)
         self.fine_logit_weights = nn.Parameter(torch.randn(num_fine_quantizers, codebook_size, dim))
@@ -229,6 +253,32 @@ class FineTransformer(_TokenTransformer):
         logits, (new_kv, new_emb) = self.forward(*args, cond_drop_prob=0.0, return_cache=True, kv_cache=kv,
                                                  embed_cache=emb, **kwargs)
         return (logits, (new_kv[None], new_emb[None])) if return_kv_cache else logits
+
+    def _pos_bias_index(self, n, nf, dev):
+        """(idx int32 [L, L], mlp inputs fp32 [P, 2]) of the engineered coarse/fine bias (:1229-1298).
+
+        Token t has a frame position and a quantizer offset (fine offsets follow the coarse ones); the bias of
+        (i, j) is the MLP at (frame_i - frame_j, offset_i - offset_j), shifted to non-negative table
+        coordinates; rows / columns of the two start tokens use `null_pos_bias` (idx -1)."""
+        key = (n, nf, str(dev))
+        if self._bias_idx.get("key") != key:
+            qc, qf = self.num_coarse_quantizers, self.num_fine_quantizers
+            max_seq = max(ceil_div(n, qc), ceil_div(nf, qf))
+            num_off = qc + qf
+            rel_off = 2 * num_off - 1
+            ar = lambda m: torch.arange(m, device=dev)  # noqa: E731
+            minus1 = torch.full((1,), -1, device=dev)
+            zero = torch.zeros(1, dtype=torch.long, device=dev)
+            pos = torch.cat((minus1, ar(n) // qc, minus1, ar(nf) // qf))
+            off = torch.cat((zero, ar(n) % qc, zero, ar(nf) % qf + qc))
+            pc = pos.clamp(min=0)
+            idx = (pc[:, None] - pc[None, :] + max_seq - 1) * rel_off + (off[:, None] - off[None, :] + num_off - 1)
+            start = pos == -1
+            idx[start[:, None] | start[None, :]] = -1
+            rows = ar((2 * max_seq - 1) * rel_off)
+            mlp_in = torch.stack((rows // rel_off, rows % rel_off), dim=-1).float()
+            self._bias_idx = dict(key=key, val=(idx.to(torch.int32).contiguous(), mlp_in))
+        return self._bias_idx["val"]
 
     def forward(self, coarse_token_ids, fine_token_ids, text=None, text_embeds=None, cond_drop_prob=None,
                 self_attn_mask=None, kv_cache=None, embed_cache=None, return_cache=False,
@@ -251,8 +301,14 @@ class FineTransformer(_TokenTransformer):
         fine = self.fine_embedding(fine_token_ids + fq * self.codebook_size) + self.fine_quantize_embedding.weight[fq]
         tokens = torch.cat((self.coarse_start_token.expand(b, 1, -1), coarse,
                             self.fine_start_token.expand(b, 1, -1), fine), dim=1)
-        tokens, new_kv = self.transformer(tokens, self_attn_mask=self_attn_mask, kv_cache=kv_cache,
-                                          return_kv_cache=True)
+        attn_bias = None
+        if exists(self.pos_bias_mlp):
+            idx, mlp_in = self._pos_bias_index(n, nf, dev)
+            m = self.pos_bias_mlp
+            table = mlp_table(mlp_in, m[0], [m[2]], m[4], self._bias_cache, "pos")
+            attn_bias = gather_bias(table, self.null_pos_bias, idx)
+        tokens, new_kv = self.transformer(tokens, self_attn_mask=self_attn_mask, attn_bias=attn_bias,
+                                          kv_cache=kv_cache, return_kv_cache=True)
         if exists(embed_cache):
             tokens = torch.cat((embed_cache.to(tokens.dtype), tokens), dim=-2)
         new_embed_cache = tokens

@@ -27,6 +27,9 @@ struct AttnBwdParams {
   const float* lse;      // [b, h, n_q_pad]  log2-domain LSE (m + log2 l) as written by the forward
   const float* delta;    // [b, h, n_q_pad]
   const uint8_t* kmask;  // [b, n_k] or null
+  const float* bias;     // [h, n_q, bias_rs] additive score bias (as given to the forward) or null
+  float* dbias;          // same layout, fp32: d(bias) is ACCUMULATED (red.add) over batches / calls; or null
+  long long bias_hs, bias_rs;
   __nv_bfloat16* dq;     // [b, n_q, h*64], row stride lddq
   __nv_bfloat16* dk;     // [b, n_k, 64], row stride lddk
   __nv_bfloat16* dv;
@@ -65,6 +68,7 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* tiles, int row, int col8,
 // ================================================================================================
 constexpr int DKV_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2 + 2) + AB_STAGES * 2 * 512 + 256;
 
+template <bool HAS_BIAS>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -196,6 +200,8 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int it = 0; it < n_iter; ++it) {
       const int qb = qb_min + it % q_per_head;
       const int q0 = qb * AB_T;
+      [[maybe_unused]] const long long bias_base =
+          HAS_BIAS ? (long long)(it / q_per_head) * p.bias_hs + min(kj, p.n_k - 1) : 0;
       mbar_wait(&qdo_full[stage], phase);  // lse / delta staged in smem
       mbar_wait(s_full, it & 1);           // S^T, dP^T ready; previous P^T/dS^T operands consumed
       tc_fence_after_sync();
@@ -219,9 +225,19 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const int qi = q0 + col;
             const bool ok = key_ok && (tile_full || (qi < p.n_q && (!p.causal || kj <= qi + off)));
             const float s = __uint_as_float(rs[g * 8 + e]);
-            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, -lse_s[col])) : 0.f;
+            float shift = -lse_s[col];
+            [[maybe_unused]] long long bidx = 0;
+            if constexpr (HAS_BIAS) {  // lanes hold consecutive keys of one query row: coalesced
+              bidx = bias_base + (long long)min(qi, p.n_q - 1) * p.bias_rs;
+              shift = fmaf(__ldg(p.bias + bidx), LOG2E, shift);
+            }
+            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, shift)) : 0.f;
             pv[e] = pe;
-            dsv[e] = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - del_s[col]) * p.scale : 0.f;
+            const float ds = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - del_s[col]) : 0.f;
+            dsv[e] = ds * p.scale;
+            if constexpr (HAS_BIAS) {
+              if (ok && p.dbias != nullptr) atomicAdd(p.dbias + bidx, ds);
+            }
           }
           store_a_chunk(sPT, row, c * 4 + g, pv);
           store_a_chunk(sdST, row, c * 4 + g, dsv);
@@ -278,6 +294,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // ================================================================================================
 constexpr int DQ_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + 256;
 
+template <bool HAS_BIAS>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -390,6 +407,8 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float delta = p.delta[roff];
     const int q_limit = p.causal ? qi + off : p.n_k - 1;
     const uint8_t* mrow = p.kmask ? p.kmask + (size_t)batch * p.n_k : nullptr;
+    [[maybe_unused]] const float* brow =
+        HAS_BIAS ? p.bias + (long long)head * p.bias_hs + (long long)min(qi, p.n_q - 1) * p.bias_rs : nullptr;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
@@ -406,6 +425,16 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float dsv[8];
+          [[maybe_unused]] float bb[8];
+          if constexpr (HAS_BIAS) {
+            const int col = kbase + c * 32 + g * 8;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            // bias_rs is a multiple of 4: each float4 is either fully inside the padded row or skipped
+            if (col + 3 < p.bias_rs) b0 = __ldg(reinterpret_cast<const float4*>(brow + col));
+            if (col + 7 < p.bias_rs) b1 = __ldg(reinterpret_cast<const float4*>(brow + col + 4));
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+            bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int kj = kbase + c * 32 + g * 8 + e;
@@ -415,7 +444,9 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
               if (ok && mrow != nullptr) ok = mrow[kj] != 0;
             }
             const float s = __uint_as_float(rs[g * 8 + e]);
-            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, -lse)) : 0.f;
+            float shift = -lse;
+            if constexpr (HAS_BIAS) shift = fmaf(bb[e], LOG2E, shift);
+            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, shift)) : 0.f;
             dsv[e] = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - delta) * p.scale : 0.f;
           }
           store_a_chunk(sdS, row, c * 4 + g, dsv);
@@ -466,13 +497,20 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 extern "C" int alm_mqa_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride,
                                 const void* v, int64_t ldv, int64_t v_bstride, const void* d_o, int64_t lddo,
                                 const void* key_mask, const float* lse, const float* delta, int n_q_pad, void* dq,
-                                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int b, int h, int n_q,
+                                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, const float* bias,
+                                float* dbias, int64_t bias_hstride, int64_t bias_rstride, int b, int h, int n_q,
                                 int n_k, int causal, float scale, alm_stream_t stream_) {
   using namespace alm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(q && k && v && d_o && lse && delta && dq && dk && dv, ALM_ERR_ARG);
   ALM_REQUIRE(b > 0 && h > 0 && n_q > 0 && n_k >= n_q, ALM_ERR_ARG);
   ALM_REQUIRE(n_q_pad % AB_T == 0 && n_q_pad >= n_q, ALM_ERR_ARG);
+  if (bias != nullptr) {
+    ALM_REQUIRE(bias_rstride >= n_k && bias_rstride % 4 == 0 && bias_hstride % 4 == 0, ALM_ERR_ALIGN);
+    ALM_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15u) == 0, ALM_ERR_ALIGN);
+  } else {
+    ALM_REQUIRE(dbias == nullptr, ALM_ERR_ARG);
+  }
   ALM_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 &&
                   lddv % 8 == 0 && k_bstride % 8 == 0 && v_bstride % 8 == 0,
               ALM_ERR_ALIGN);
@@ -504,21 +542,30 @@ extern "C" int alm_mqa_attn_bwd(const void* q, int64_t ldq, const void* k, int64
   p.kmask = reinterpret_cast<const uint8_t*>(key_mask);
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  p.bias = bias; p.dbias = dbias; p.bias_hs = bias_hstride; p.bias_rs = bias_rstride;
   p.b = b; p.h = h; p.n_q = n_q; p.n_k = n_k; p.n_q_pad = n_q_pad;
   p.causal = causal;
   p.scale = scale;
   p.scale_log2 = scale * LOG2E;
   static bool attr_set = false;
   if (!attr_set) {
-    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
   dim3 grid_kv(((n_k + AB_T - 1) / AB_T) * b);
-  mqa_attn_bwd_dkv_kernel<<<grid_kv, AB_THREADS, DKV_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  if (bias != nullptr)
+    mqa_attn_bwd_dkv_kernel<true><<<grid_kv, AB_THREADS, DKV_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  else
+    mqa_attn_bwd_dkv_kernel<false><<<grid_kv, AB_THREADS, DKV_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
   ALM_CHECK_LAUNCH();
   dim3 grid_q((n_q + AB_T - 1) / AB_T, h, b);
-  mqa_attn_bwd_dq_kernel<<<grid_q, AB_THREADS, DQ_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  if (bias != nullptr)
+    mqa_attn_bwd_dq_kernel<true><<<grid_q, AB_THREADS, DQ_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  else
+    mqa_attn_bwd_dq_kernel<false><<<grid_q, AB_THREADS, DQ_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(2);
   return ALM_OK;

@@ -27,12 +27,21 @@ struct AttnFwdParams {
   __nv_bfloat16* o;       // [b, n_q, h*64] row stride ldo
   float* lse;             // [b, h, lse_stride] log2-domain LSE of the scaled scores (for backward); may be null
   const uint8_t* kmask;   // [b, n_k] 1 = attend, 0 = masked; may be null
+  const float* bias;      // [h, n_q, bias_rs] additive score bias (natural-log domain, added after the scale); may be null
+  long long bias_hs, bias_rs;  // element strides between heads / query rows (bias_rs % 4 == 0, >= n_k)
   long long ldo, lse_stride;
   int b, h, n_q, n_k;
   int causal;
   float scale_log2;       // d^-1/2 * log2(e)
 };
 
+__device__ __forceinline__ float att_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool HAS_BIAS>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -169,45 +178,64 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int e = 0; e < 32; ++e) o_acc[e] = fmaf(o_acc[e], a, __uint_as_float(r[e]));
     };
 
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float* brow = nullptr;  // this query row of the bias (rows past n_q are clamped: their output is dropped)
+    if constexpr (HAS_BIAS)
+      brow = p.bias + (long long)head * p.bias_hs + (long long)min(qi, p.n_q - 1) * p.bias_rs;
+    // bias values of 4 consecutive keys, pre-multiplied into the log2 domain; columns past the padded row read 0
+    auto bias4 = [&](int col) -> float4 {
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (HAS_BIAS) {
+        if (col + 3 < p.bias_rs) bv = __ldg(reinterpret_cast<const float4*>(brow + col));
+        bv.x *= kLog2e; bv.y *= kLog2e; bv.z *= kLog2e; bv.w *= kLog2e;
+      }
+      return bv;
+    };
+
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
       const int kbase = j * ATT_BN;
+      // CTA-uniform: every row of the block sees every key of this tile (no key mask, fully below the diagonal)
+      const bool tile_full = mrow == nullptr && kbase + ATT_BN <= p.n_k && (!p.causal || kbase + ATT_BN - 1 <= q0 + off);
       // key validity bits of the whole 128-key tile (the row max needs all of it)
       uint32_t valid[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-      if (mrow != nullptr) {
+      if (!tile_full) {
+        if (mrow != nullptr) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              const int kk = kbase + w * 32 + q4 * 16;
+              uint4 mv = make_uint4(0, 0, 0, 0);
+              if (kk + 16 <= p.n_k && ((reinterpret_cast<uintptr_t>(mrow + kk) & 15u) == 0)) {
+                mv = __ldg(reinterpret_cast<const uint4*>(mrow + kk));
+              } else {
+                uint8_t tmp[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) tmp[e] = (kk + e < p.n_k) ? __ldg(mrow + kk + e) : 0;
+                mv = *reinterpret_cast<uint4*>(tmp);
+              }
+              const uint32_t words[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if ((words[e >> 2] >> ((e & 3) * 8)) & 0xFFu) bits |= 1u << (q4 * 16 + e);
+            }
+            valid[w] = bits;
+          }
+        }
+        const int lim = min(q_limit, p.n_k - 1) - kbase;  // keys 0..lim of this tile are in range
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          uint32_t bits = 0;
-#pragma unroll
-          for (int q4 = 0; q4 < 2; ++q4) {
-            const int kk = kbase + w * 32 + q4 * 16;
-            uint4 mv = make_uint4(0, 0, 0, 0);
-            if (kk + 16 <= p.n_k && ((reinterpret_cast<uintptr_t>(mrow + kk) & 15u) == 0)) {
-              mv = __ldg(reinterpret_cast<const uint4*>(mrow + kk));
-            } else {
-              uint8_t tmp[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) tmp[e] = (kk + e < p.n_k) ? __ldg(mrow + kk + e) : 0;
-              mv = *reinterpret_cast<uint4*>(tmp);
-            }
-            const uint32_t words[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if ((words[e >> 2] >> ((e & 3) * 8)) & 0xFFu) bits |= 1u << (q4 * 16 + e);
-          }
-          valid[w] = bits;
+          const int hi = lim - w * 32;
+          const uint32_t range = hi >= 31 ? 0xFFFFFFFFu : (hi < 0 ? 0u : ((2u << hi) - 1u));
+          valid[w] &= range;
         }
       }
-      const int lim = min(q_limit, p.n_k - 1) - kbase;  // keys 0..lim of this tile are in range
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int hi = lim - w * 32;
-        const uint32_t range = hi >= 31 ? 0xFFFFFFFFu : (hi < 0 ? 0u : ((2u << hi) - 1u));
-        valid[w] &= range;
-      }
       // pass 1: row max over all 128 keys (both warps of a quadrant compute it redundantly: TMEM reads are
-      // cheap, and it avoids a cross-warp exchange); pass 2 below only touches this warp's 64 columns
+      // cheap, and it avoids a cross-warp exchange); pass 2 below only touches this warp's 64 columns.
+      // m_tile is in the log2 domain when a bias is present, else raw (scaled once after the loop).
       float m_tile = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -215,20 +243,36 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, r);
         tmem_ld_wait();
+        if constexpr (HAS_BIAS) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if ((valid[c] >> e) & 1u) m_tile = fmaxf(m_tile, __uint_as_float(r[e]));
+          for (int g = 0; g < 8; ++g) {
+            const float4 bv = bias4(kbase + c * 32 + g * 4);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float sv = fmaf(__uint_as_float(r[g * 4 + e]), p.scale_log2, bb[e]);
+              if (tile_full || ((valid[c] >> (g * 4 + e)) & 1u)) m_tile = fmaxf(m_tile, sv);
+            }
+          }
+        } else if (tile_full) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m_tile = fmaxf(m_tile, __uint_as_float(r[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if ((valid[c] >> e) & 1u) m_tile = fmaxf(m_tile, __uint_as_float(r[e]));
+        }
       }
-      const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
+      const float m_new = fmaxf(m_run, HAS_BIAS ? m_tile : m_tile * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);  // m_run == -inf -> 0
+      const float alpha = att_ex2(m_run - m_use);  // m_run == -inf -> 0
       // previous tile's P V must be consumed before sP is overwritten
       if (j > 0) {
         mbar_wait(pv_full, (j - 1) & 1);
         tc_fence_after_sync();
         add_pv(alpha_prev);
       }
-      // pass 2: p = exp2(s*scale - m) -> bf16 P in the SW128 K-major A-operand layout
+      // pass 2: p = exp2(s*scale + bias - m) -> bf16 P in the SW128 K-major A-operand layout
       float l_tile = 0.f;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -237,12 +281,34 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld_32x32b_x32(tmem_S + lane_sel + half * 64 + cc * 32, r);
         tmem_ld_wait();
         float pe[32];
+        if constexpr (HAS_BIAS) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float pv =
-              ((valid[half * 2 + cc] >> e) & 1u) ? exp2f(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_use)) : 0.f;
-          pe[e] = pv;
-          l_tile += pv;
+          for (int g = 0; g < 8; ++g) {
+            const float4 bv = bias4(kbase + half * 64 + cc * 32 + g * 4);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool ok = tile_full || ((valid[half * 2 + cc] >> (g * 4 + e)) & 1u);
+              const float pv = ok ? att_ex2(fmaf(__uint_as_float(r[g * 4 + e]), p.scale_log2, bb[e]) - m_use) : 0.f;
+              pe[g * 4 + e] = pv;
+              l_tile += pv;
+            }
+          }
+        } else if (tile_full) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float pv = att_ex2(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_use));
+            pe[e] = pv;
+            l_tile += pv;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float pv = ((valid[half * 2 + cc] >> e) & 1u)
+                                 ? att_ex2(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_use)) : 0.f;
+            pe[e] = pv;
+            l_tile += pv;
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -302,8 +368,8 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride,
                                 const void* v, int64_t ldv, int64_t v_bstride, const void* key_mask, void* o,
-                                int64_t ldo, float* lse, int64_t lse_stride, int b, int h, int n_q, int n_k, int causal,
-                                float scale,
+                                int64_t ldo, float* lse, int64_t lse_stride, const float* bias, int64_t bias_hstride,
+                                int64_t bias_rstride, int b, int h, int n_q, int n_k, int causal, float scale,
                                 alm_stream_t stream_) {
   using namespace alm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -312,6 +378,10 @@ extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64
   ALM_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, ALM_ERR_ALIGN);
   ALM_REQUIRE(k_bstride % 8 == 0 && v_bstride % 8 == 0, ALM_ERR_ALIGN);
   ALM_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15u) == 0, ALM_ERR_ALIGN);
+  if (bias != nullptr) {
+    ALM_REQUIRE(bias_rstride >= n_k && bias_rstride % 4 == 0 && bias_hstride % 4 == 0, ALM_ERR_ALIGN);
+    ALM_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15u) == 0, ALM_ERR_ALIGN);
+  }
 
   CUtensorMap tmQ, tmK, tmV;
   {
@@ -336,6 +406,9 @@ extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
   p.kmask = reinterpret_cast<const uint8_t*>(key_mask);
+  p.bias = bias;
+  p.bias_hs = bias_hstride;
+  p.bias_rs = bias_rstride;
   p.ldo = ldo;
   p.lse_stride = lse_stride;
   p.b = b; p.h = h; p.n_q = n_q; p.n_k = n_k;
@@ -343,12 +416,17 @@ extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64
   p.scale_log2 = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ATT_SMEM_BYTES));
+    ALM_CUDA_OK(cudaFuncSetAttribute(mqa_attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      ATT_SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((n_q + ATT_BM - 1) / ATT_BM, h, b);
-  mqa_attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  if (bias != nullptr)
+    mqa_attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  else
+    mqa_attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;

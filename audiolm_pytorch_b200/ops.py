@@ -109,15 +109,23 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, alpha=1.0, b
     return out
 
 
-def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, return_lse=True):
+def _check_bias(bias, heads, n_q, n_k):
+    """bias: fp32 [heads, n_q, ld] view with ld >= n_k, ld % 4 == 0 (see `pad_bias`)."""
+    assert bias.dtype == f32 and bias.dim() == 3 and bias.shape[0] == heads and bias.shape[1] == n_q
+    assert bias.shape[2] >= n_k and bias.stride(2) == 1 and bias.stride(1) % 4 == 0 and bias.stride(0) % 4 == 0
+    return bias.stride(0), bias.stride(1)
+
+
+def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, return_lse=True, bias=None):
     """Multi-query attention forward (attend.py:69-146).
 
     q: [b, n_q, heads*64] bf16 (last dim contiguous; may be a column slice of a wider buffer)
     k, v: [b, n_k, 64] bf16 (one shared head);  key_mask: [b, n_k] bool/uint8 (True = attend) or None.
     Queries are right-aligned against keys (query i sees keys <= i + n_k - n_q) when causal.
+    bias: optional fp32 [heads, n_q, >=n_k] additive score bias shared by the batch (attend.py:122-124).
     Returns o [b, n_q, heads*64] bf16 and lse [b, heads, n_q] fp32.
     """
-    _check_cuda(q, k, v, key_mask)
+    _check_cuda(q, k, v, key_mask, bias)
     assert q.dtype == bf16 and k.dtype == bf16 and v.dtype == bf16
     b, n_q, hd = q.shape
     n_k = k.shape[1]
@@ -134,21 +142,23 @@ def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, retu
         scale = 64 ** -0.5
     # algorithmic FLOPs: QK^T + PV over the visible (lower-triangle) part only
     vis = (n_q * n_k - n_q * (n_q - 1) / 2) if causal else n_q * n_k
+    bhs, brs = _check_bias(bias, heads, n_q, n_k) if bias is not None else (0, 0)
     with _timed("mqa_attn_fwd_tcgen05", 4.0 * b * heads * 64 * vis):
         _lib.call(
             "alm_mqa_attn_fwd",
             q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), key_mask,
-            o, o.stride(1), lse, n_q_pad, b, heads, n_q, n_k, int(causal), float(scale),
+            o, o.stride(1), lse, n_q_pad, bias, bhs, brs, b, heads, n_q, n_k, int(causal), float(scale),
         )
     return o, lse
 
 
-def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, scale=None):
+def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, scale=None, bias=None, dbias=None):
     """Backward of mqa_attn_fwd: returns dq [b,n_q,h*64], dk [b,n_k,64], dv [b,n_k,64] (bf16).
 
-    lse is the padded [b, heads, n_q_pad] tensor returned by the forward.
+    lse is the padded [b, heads, n_q_pad] tensor returned by the forward.  With a bias, d(bias) is ACCUMULATED
+    into `dbias` (fp32, same shape/strides as `bias`; the caller zeroes it once per step).
     """
-    _check_cuda(q, k, v, o, d_o, lse, key_mask)
+    _check_cuda(q, k, v, o, d_o, lse, key_mask, bias, dbias)
     b, n_q, hd = q.shape
     n_k = k.shape[1]
     n_q_pad = lse.shape[-1]
@@ -163,15 +173,43 @@ def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, sca
     dq = torch.empty(b, n_q, hd, device=q.device, dtype=bf16)
     dk = torch.empty(b, n_k, 64, device=q.device, dtype=bf16)
     dv = torch.empty(b, n_k, 64, device=q.device, dtype=bf16)
+    bhs, brs = _check_bias(bias, heads, n_q, n_k) if bias is not None else (0, 0)
+    if dbias is not None:
+        assert bias is not None and dbias.dtype == f32 and dbias.shape == bias.shape and dbias.stride() == bias.stride()
     vis = (n_q * n_k - n_q * (n_q - 1) / 2) if causal else n_q * n_k
     with _timed("mqa_attn_bwd_tcgen05", 10.0 * b * heads * 64 * vis):  # 5 matmuls (algorithmic; 7 executed)
         _lib.call(
             "alm_mqa_attn_bwd",
             q, q.stride(1), k, k.stride(1), k.stride(0), v, v.stride(1), v.stride(0), d_o, d_o.stride(1), key_mask,
             lse, delta, n_q_pad, dq, dq.stride(1), dk, dk.stride(1), dv, dv.stride(1),
-            b, heads, n_q, n_k, int(causal), float(scale),
+            bias, dbias, bhs, brs, b, heads, n_q, n_k, int(causal), float(scale),
         )
     return dq, dk, dv
+
+
+def bias_gather_fwd(table, idx, override, *, ld=None):
+    """table [P, H] fp32, idx [n_q, n_k] int32 (-1 = override), override [H] fp32 or None -> bias [H, n_q, ld] fp32."""
+    _check_cuda(table, idx, override)
+    assert table.dtype == f32 and table.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+    H = table.shape[1]
+    n_q, n_k = idx.shape
+    ld = (n_k + 3) // 4 * 4 if ld is None else ld
+    out = torch.empty(H, n_q, ld, device=table.device, dtype=f32)
+    _lib.call("alm_bias_gather_fwd", table, idx, None if override is None else override.contiguous(), out, H, n_q,
+              n_k, ld)
+    return out
+
+
+def bias_gather_bwd(dbias, idx, table_rows, *, want_override):
+    """scatter-add of d(bias) [H, n_q, ld] back to the table rows / the per-head override scalar."""
+    _check_cuda(dbias, idx)
+    assert dbias.dtype == f32 and dbias.is_contiguous()
+    H, n_q, ld = dbias.shape
+    n_k = idx.shape[1]
+    dtable = torch.zeros(table_rows, H, device=dbias.device, dtype=f32)
+    dover = torch.zeros(H, device=dbias.device, dtype=f32) if want_override else None
+    _lib.call("alm_bias_gather_bwd", dbias, idx, dtable, dover, H, n_q, n_k, ld)
+    return dtable, dover
 
 
 HC_AUX = 30  # floats of per-token state kept for the backward (see csrc/hyper_conn.cu)

@@ -56,12 +56,14 @@ class Attend(nn.Module):
 
     def forward(self, q, k, v, mask=None, attn_bias=None):
         """q [b h n 64], k/v [b j 64] -> [b h n 64] (inference helper; training goes through Transformer)."""
-        if exists(attn_bias):
-            raise NotImplementedError("additive attention bias (rel_pos_bias path) is not built yet")
         b, h, n, d = q.shape
+        if exists(attn_bias):
+            assert not self.flash, "attention bias not supported for flash attention"  # attend.py:112
+            from .rel_pos import as_kernel_bias
+            attn_bias = as_kernel_bias(attn_bias.detach())
         qf = q.permute(0, 2, 1, 3).reshape(b, n, h * d).to(bf16).contiguous()
         o, _ = ops.mqa_attn_fwd(qf, k.to(bf16).contiguous(), v.to(bf16).contiguous(), heads=h, key_mask=mask,
-                                causal=self.causal, return_lse=False)
+                                causal=self.causal, return_lse=False, bias=attn_bias)
         return o.reshape(b, n, h, d).permute(0, 2, 1, 3)
 
 
@@ -205,10 +207,11 @@ class _StackFn(torch.autograd.Function):
     """Whole Transformer stack as one autograd node: explicit forward + backward over C-ABI kernels."""
 
     @staticmethod
-    def forward(ctx, tr, x, mask, *params):
-        out, saved = tr._run_forward(x, mask, save=any(ctx.needs_input_grad))
+    def forward(ctx, tr, x, mask, bias, *params):
+        out, saved = tr._run_forward(x, mask, bias, save=any(ctx.needs_input_grad))
         ctx.tr = tr
         ctx.saved = saved
+        ctx.bias_grad = bias is not None and ctx.needs_input_grad[3]
         kv = saved["kv"]
         ctx.mark_non_differentiable(kv)
         return out, kv
@@ -216,9 +219,13 @@ class _StackFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dkv):
         tr = ctx.tr
-        dx, grads = tr._run_backward(ctx.saved, dout)
+        S = ctx.saved
+        # d(bias) is accumulated by every layer's attention backward (atomic adds over batches and layers)
+        S["dbias"] = torch.zeros_like(S["bias"]) if ctx.bias_grad else None
+        dx, grads = tr._run_backward(S, dout)
+        dbias = S["dbias"]
         ctx.saved = None
-        return (None, dx, None, *grads)
+        return (None, dx, None, dbias, *grads)
 
 
 def _grad_targets(params):
@@ -264,8 +271,11 @@ class Transformer(nn.Module):
         self.grad_shrink_alpha = grad_shrink_alpha
         self.num_residual_streams = num_residual_streams
         self.add_value_residual = add_value_residual
-        self.rel_pos_bias = None
-        self._wants_rel_pos_bias = rel_pos_bias
+        if rel_pos_bias:
+            from .rel_pos import RelativePositionBias  # (rel_pos imports heads, which imports this module)
+            self.rel_pos_bias = RelativePositionBias(dim=dim // 2, heads=heads)
+        else:
+            self.rel_pos_bias = None
 
         self.layers = nn.ModuleList([])
         if num_residual_streams == 1:
@@ -326,23 +336,27 @@ class Transformer(nn.Module):
                 return_kv_cache=False, kv_cache=None):
         if exists(context):
             raise NotImplementedError("conditioning context is outside the accelerated hot path")
-        if exists(attn_bias) or self._wants_rel_pos_bias:
-            raise NotImplementedError(
-                "relative-position / additive attention bias (flash_attn=False path) is not built yet; "
-                "construct the transformer with flash_attn=True")
         if not x.is_cuda:
             raise ops._lib.AlmError("Transformer needs CUDA tensors (no CPU fallback)")
+        # relative positional bias over the FULL sequence, then the rows of the new tokens (:497-506)
+        n = x.shape[1]
+        bias = attn_bias if exists(attn_bias) else (self.rel_pos_bias(n, n) if exists(self.rel_pos_bias) else None)
+        if exists(bias):
+            from .rel_pos import as_kernel_bias
+            bias = as_kernel_bias(bias)
         if exists(kv_cache):
-            out, kv = self._forward_cached(x, self_attn_mask, kv_cache)
+            if exists(bias):
+                bias = bias[:, kv_cache.shape[-2]:, :]
+            out, kv = self._forward_cached(x, self_attn_mask, kv_cache, bias)
         else:
-            out, kv = _StackFn.apply(self, x, self_attn_mask, *self._param_list())
+            out, kv = _StackFn.apply(self, x, self_attn_mask, bias, *self._param_list())
         if not return_kv_cache:
             return out
         return out, kv
 
-    def _run_forward(self, x, mask, save):
+    def _run_forward(self, x, mask, bias, save):
         if self.num_residual_streams == 1:
-            return self._run_forward_plain(x, mask, save)
+            return self._run_forward_plain(x, mask, bias, save)
         b, n, d = x.shape
         M = b * n
         H = self.heads
@@ -366,7 +380,7 @@ class Transformer(nn.Module):
                 v_first = kv[:, 64:].clone()               # layer-0 values before any mixing (:355-358)
             k3 = kv[:, :64].unflatten(0, (b, n))
             v3 = kv[:, 64:].unflatten(0, (b, n))
-            o, lse = ops.mqa_attn_fwd(q.view(b, n, H * 64), k3, v3, heads=H, key_mask=mask_u8, causal=True)
+            o, lse = ops.mqa_attn_fwd(q.view(b, n, H * 64), k3, v3, heads=H, key_mask=mask_u8, causal=True, bias=bias)
             o2 = o.view(M, H * 64)
             Y = ops.gemm(o2, W["wo"])
             rec.update(q=q, kv=kv, o=o2, lse=lse, Y_a=Y)
@@ -388,7 +402,7 @@ class Transformer(nn.Module):
         kv_t = torch.stack([kv.view(b, n, 2, 64).permute(2, 0, 1, 3) for kv in kvs])
         saved = dict(kv=kv_t)
         if save:
-            saved.update(L=L, x2=x2, mask=mask_u8, stats=stats, shape=(b, n, d), x_dtype=x.dtype)
+            saved.update(L=L, x2=x2, mask=mask_u8, bias=bias, stats=stats, shape=(b, n, d), x_dtype=x.dtype)
         return out.view(b, n, d), saved
 
     # ---- backward ------------------------------------------------------------------------------
@@ -443,7 +457,8 @@ class Transformer(nn.Module):
             k3 = kv[:, :64].unflatten(0, (b, n))
             v3 = kv[:, 64:].unflatten(0, (b, n))
             dq, dk, dv = ops.mqa_attn_bwd(rec["q"].view(b, n, H * 64), k3, v3, rec["o"].view(b, n, H * 64),
-                                          dO.view(b, n, H * 64), rec["lse"], heads=H, key_mask=S["mask"], causal=True)
+                                          dO.view(b, n, H * 64), rec["lse"], heads=H, key_mask=S["mask"], causal=True,
+                                          bias=S["bias"], dbias=S["dbias"])
             dkv = torch.empty(M, 128, device=dev, dtype=bf16)
             ops.axpby(dk.view(M, 64), 1.0, None, 0.0, out=dkv[:, :64])
             dv2 = dv.view(M, 64)
@@ -472,7 +487,7 @@ class Transformer(nn.Module):
 
 
     # ---- num_residual_streams == 1: plain residual stream (fp32) ---------------------------------
-    def _attn_branch_fwd(self, i, xn, raw, b, n, mask_u8, v_first, cache=None):
+    def _attn_branch_fwd(self, i, xn, raw, b, n, mask_u8, v_first, cache=None, bias=None):
         """q/kv projections, value residual, (optional KV cache), attention, output projection."""
         H = self.heads
         W = self._weights(i)
@@ -488,12 +503,12 @@ class Transformer(nn.Module):
         if cache is not None:
             k3 = torch.cat((cache[0].to(bf16), k3), dim=1).contiguous()
             v3 = torch.cat((cache[1].to(bf16), v3), dim=1).contiguous()
-        o, lse = ops.mqa_attn_fwd(q.view(b, n, H * 64), k3, v3, heads=H, key_mask=mask_u8, causal=True)
+        o, lse = ops.mqa_attn_fwd(q.view(b, n, H * 64), k3, v3, heads=H, key_mask=mask_u8, causal=True, bias=bias)
         o2 = o.view(M, H * 64)
         Y = ops.gemm(o2, W["wo"])
         return q, kv, o2, lse, Y, v_first, torch.stack((k3, v3))
 
-    def _run_forward_plain(self, x, mask, save, kv_cache=None):
+    def _run_forward_plain(self, x, mask, bias, save, kv_cache=None):
         b, n, d = x.shape
         M = b * n
         r = x.detach().reshape(M, d).to(f32).contiguous()
@@ -508,7 +523,7 @@ class Transformer(nn.Module):
             W = self._weights(i)
             inner, ip = f.inner, _pad8(f.inner)
             q, kv, o2, lse, Y, v_first, kv_t = self._attn_branch_fwd(
-                i, xn, raw, b, n, mask_u8, v_first, None if kv_cache is None else kv_cache[i])
+                i, xn, raw, b, n, mask_u8, v_first, None if kv_cache is None else kv_cache[i], bias)
             kvs.append(kv_t)
             r_f, xn_f, _, st_f = ops.resid_ln_fwd(r, Y, getattr(f, "0").gamma)
             h = ops.gemm(xn_f, W["w1"])
@@ -522,7 +537,8 @@ class Transformer(nn.Module):
         r_last, out, _, st_last = ops.resid_ln_fwd(r_f, Y2, self.norm.gamma)
         saved = dict(kv=torch.stack(kvs))
         if save:
-            saved.update(L=L, mask=mask_u8, r_last=r_last, st_last=st_last, shape=(b, n, d), x_dtype=x.dtype)
+            saved.update(L=L, mask=mask_u8, bias=bias, r_last=r_last, st_last=st_last, shape=(b, n, d),
+                         x_dtype=x.dtype)
         return out.view(b, n, d), saved
 
     def _run_backward_plain(self, S, dout):
@@ -558,7 +574,8 @@ class Transformer(nn.Module):
             k3 = kv[:, :64].unflatten(0, (b, n))
             v3 = kv[:, 64:].unflatten(0, (b, n))
             dq, dk, dv = ops.mqa_attn_bwd(rec["q"].view(b, n, H * 64), k3, v3, rec["o"].view(b, n, H * 64),
-                                          dO.view(b, n, H * 64), rec["lse"], heads=H, key_mask=S["mask"], causal=True)
+                                          dO.view(b, n, H * 64), rec["lse"], heads=H, key_mask=S["mask"], causal=True,
+                                          bias=S["bias"], dbias=S["dbias"])
             dkv = torch.empty(M, 128, device=dev, dtype=bf16)
             ops.axpby(dk.view(M, 64), 1.0, None, 0.0, out=dkv[:, :64])
             dv2 = dv.view(M, 64)
@@ -580,12 +597,12 @@ class Transformer(nn.Module):
 
     # ---- incremental (KV-cache) inference ------------------------------------------------------
     @torch.no_grad()
-    def _forward_cached(self, x, mask, kv_cache):
+    def _forward_cached(self, x, mask, kv_cache, bias=None):
         """x is the FULL sequence; only x[:, cache_len:] is processed (audiolm_pytorch.py:489-496)."""
         cache_len = kv_cache.shape[-2]
         x = x[:, cache_len:]
         if self.num_residual_streams == 1:
-            out, saved = self._run_forward_plain(x, mask, save=False, kv_cache=kv_cache)
+            out, saved = self._run_forward_plain(x, mask, bias, save=False, kv_cache=kv_cache)
             return out, saved["kv"]
         b, n, d = x.shape
         M = b * n
@@ -611,7 +628,7 @@ class Transformer(nn.Module):
             v_all = torch.cat((cv, kv[:, 64:].unflatten(0, (b, n))), dim=1).contiguous()
             new_cache.append(torch.stack((k_all, v_all)))
             o, _ = ops.mqa_attn_fwd(q.view(b, n, H * 64), k_all, v_all, heads=H, key_mask=mask_u8, causal=True,
-                                    return_lse=False)
+                                    return_lse=False, bias=bias)
             Y = ops.gemm(o.view(M, H * 64), W["wo"])
             R2, _, xn2, beta2, _ = ops.hc_pre_fwd(ff_hc.kernel_params(), getattr(f, "0").gamma, R_in=R, Y=Y,
                                                   beta_prev=beta, M=M, d=d)

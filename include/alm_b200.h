@@ -65,11 +65,16 @@ int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const v
  * (audiolm_pytorch.py:390).  Fully masked rows produce zeros (the reference's flash path yields NaN).
  * q rows stride ldq (q may be a column slice of a fused qkv buffer); k/v rows stride ldk/ldv, batch
  * strides k_bstride/v_bstride (elements).
+ * bias (optional, fp32 [h, n_q, bias_rstride], shared by all batches): added to the scaled scores before the
+ * masks, i.e. the `sim = sim + attn_bias` of the non-flash path (attend.py:122-124) fed by
+ * RelativePositionBias / cross_attn_bias / pos_bias_mlp (audiolm_pytorch.py:202-242, 926-936, 1229-1298).
+ * bias_rstride >= n_k and a multiple of 4; the backward accumulates d(bias) into dbias (same layout) with
+ * atomic adds - zero it once per step, every layer / batch adds into it.
  */
 int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride, const void* v,
                      int64_t ldv, int64_t v_bstride, const void* key_mask, void* o, int64_t ldo, float* lse,
-                     int64_t lse_stride, int b, int h, int n_q, int n_k, int causal, float scale,
-                     alm_stream_t stream);
+                     int64_t lse_stride, const float* bias, int64_t bias_hstride, int64_t bias_rstride, int b, int h,
+                     int n_q, int n_k, int causal, float scale, alm_stream_t stream);
 
 /*
  * Backward of alm_mqa_attn_fwd (two tcgen05 kernels: dK/dV per key block accumulating over all heads
@@ -79,10 +84,24 @@ int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int
 int alm_mqa_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride, const void* v,
                      int64_t ldv, int64_t v_bstride, const void* d_o, int64_t lddo, const void* key_mask,
                      const float* lse, const float* delta, int n_q_pad, void* dq, int64_t lddq, void* dk,
-                     int64_t lddk, void* dv, int64_t lddv, int b, int h, int n_q, int n_k, int causal, float scale,
+                     int64_t lddk, void* dv, int64_t lddv, const float* bias, float* dbias, int64_t bias_hstride,
+                     int64_t bias_rstride, int b, int h, int n_q, int n_k, int causal, float scale,
                      alm_stream_t stream);
 int alm_attn_delta(const void* o, int64_t ldo, const void* d_o, int64_t lddo, float* delta /* [b,h,stride] */,
                    int64_t delta_stride, int b, int h, int n, alm_stream_t stream);
+
+/*
+ * Dense attention bias from a learned table (HBM-bound gather, scatter-add backward):
+ *   out[h, i, j] = idx[i*n_k + j] >= 0 ? table[idx * heads + h] : override_h[h]     (idx == -1: override)
+ * out is fp32 [heads, n_q, ld] with ld >= n_k (pad columns are written as 0).  Replaces the `x[rel_pos]`
+ * gather of RelativePositionBias.forward (audiolm_pytorch.py:225-242), the torch.where with cross_attn_bias
+ * (:926-936) and the index-select + where with null_pos_bias of the fine transformer (:1278-1298).
+ * The backward accumulates into dtable [rows, heads] / doverride [heads] (zeroed by the caller).
+ */
+int alm_bias_gather_fwd(const float* table, const int32_t* idx, const float* override_h, float* out, int heads,
+                        int n_q, int n_k, int64_t ld, alm_stream_t stream);
+int alm_bias_gather_bwd(const float* dbias, const int32_t* idx, float* dtable, float* doverride, int heads, int n_q,
+                        int n_k, int64_t ld, alm_stream_t stream);
 
 /* ---- Hyper-Connections residual streams fused with the pre-LayerNorm (HBM-bound) ---------------- */
 /*

@@ -219,6 +219,130 @@ def golden_fine(ref):
                GOLDEN / "fine.pt")
 
 
+def golden_relpos(ref):
+    """flash_attn=False models: RelativePositionBias (semantic), + cross_attn_bias (coarse), 2-D pos_bias_mlp +
+    null_pos_bias (fine) - SURVEY §8 row a7.  Forward, masked forward, cached decode step, CE loss gradients."""
+    import torch.nn.functional as F
+    out = {}
+    print("relative position bias (flash_attn=False):")
+
+    def ce(logits, labels):
+        return F.cross_entropy(logits.transpose(1, 2), labels)
+
+    def bias_perturb(m, seed):
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if name in ("cross_attn_bias", "null_pos_bias"):
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+                elif "rel_pos_bias" in name or "pos_bias_mlp" in name:
+                    p.add_(torch.randn(p.shape, generator=g) * 0.05)
+
+    # ---- semantic ----
+    torch.manual_seed(71)
+    kw = dict(num_semantic_tokens=50, dim=64, depth=2, heads=2, flash_attn=False)
+    m = ref.lm.SemanticTransformer(**kw).eval()
+    perturb(m, 4)
+    bias_perturb(m, 5)
+    ids = torch.randint(0, 50, (2, 19))
+    labels = torch.randint(0, 51, (2, 20))
+    mask = ot.fcm_mask((2, 19), 0.15, torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        lg = m(ids=ids)
+        lgm = m(ids=ids, self_attn_mask=mask.clone())
+        l12, cache = m(ids=ids[:, :12], return_kv_cache=True)
+        inc, _ = m(ids=ids[:, :13], kv_cache=cache, return_kv_cache=True)
+    m.zero_grad()
+    loss = ce(m(ids=ids), labels)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    st = clone_state(m)
+    hk = dict(heads=2, depth=2)
+    o, _ = ot.semantic_forward(st, ids, **hk)
+    check("semantic logits", o, lg)
+    om, _ = ot.semantic_forward(st, ids, self_attn_mask=mask, **hk)
+    check("semantic logits masked", om, lgm)
+    _, oc = ot.semantic_forward(st, ids[:, :12], **hk)
+    oi, _ = ot.semantic_forward(st, ids[:, :13], kv_cache=oc, **hk)
+    check("semantic cached step", oi, inc)
+    check("semantic loss", ce(o, labels), loss.detach())
+    out["semantic"] = dict(kwargs=kw, state=st, ids=ids, labels=labels, mask=mask, logits=lg, logits_masked=lgm,
+                           logits_inc=inc, loss=loss.detach(), grads=grads)
+
+    # ---- coarse ----
+    torch.manual_seed(72)
+    kw = dict(num_semantic_tokens=50, codebook_size=64, num_coarse_quantizers=3, dim=64, depth=2, heads=2,
+              flash_attn=False)
+    m = ref.lm.CoarseTransformer(**kw).eval()
+    perturb(m, 6)
+    bias_perturb(m, 7)
+    sem = torch.randint(0, 50, (2, 10))
+    coarse = torch.randint(0, 64, (2, 22))
+    sem_labels = torch.randint(0, 51, (2, 10))
+    coarse_labels = torch.randint(0, 65, (2, 23))
+    with torch.no_grad():
+        sl, cl = m(semantic_token_ids=sem, coarse_token_ids=coarse)
+        (_, cl_a), (kv_a, emb_a) = m(semantic_token_ids=sem, coarse_token_ids=coarse[:, :9], return_cache=True,
+                                     return_only_coarse_logits=True)
+        (_, cl_b), _ = m(semantic_token_ids=sem, coarse_token_ids=coarse[:, :10], return_cache=True, kv_cache=kv_a,
+                         embed_cache=emb_a, return_only_coarse_logits=True)
+    m.zero_grad()
+    sl2, cl2 = m(semantic_token_ids=sem, coarse_token_ids=coarse)
+    loss = ce(sl2, sem_labels) + ce(cl2, coarse_labels)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    st = clone_state(m)
+    hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3)
+    (osl, ocl), _ = ot.coarse_forward(st, sem, coarse, **hk)
+    check("coarse: semantic logits", osl, sl)
+    check("coarse: coarse logits", ocl, cl)
+    (_, _), (okv_a, oemb_a) = ot.coarse_forward(st, sem, coarse[:, :9], return_only_coarse_logits=True, **hk)
+    (_, ocl_b), _ = ot.coarse_forward(st, sem, coarse[:, :10], kv_cache=okv_a, embed_cache=oemb_a,
+                                      return_only_coarse_logits=True, **hk)
+    check("coarse cached step", ocl_b, cl_b)
+    check("coarse loss", ce(osl, sem_labels) + ce(ocl, coarse_labels), loss.detach())
+    out["coarse"] = dict(kwargs=kw, state=st, sem=sem, coarse=coarse, sem_labels=sem_labels,
+                         coarse_labels=coarse_labels, sem_logits=sl, coarse_logits=cl, coarse_logits_b=cl_b,
+                         loss=loss.detach(), grads=grads)
+
+    # ---- fine ----
+    torch.manual_seed(73)
+    kw = dict(num_coarse_quantizers=3, num_fine_quantizers=5, codebook_size=64, dim=64, depth=2, heads=2,
+              flash_attn=False)
+    m = ref.lm.FineTransformer(**kw).eval()
+    perturb(m, 8)
+    bias_perturb(m, 9)
+    coarse = torch.randint(0, 64, (2, 12))
+    coarse[1, -3:] = -1
+    fine = torch.randint(0, 64, (2, 18))
+    c_labels = torch.randint(0, 64, (2, 12))
+    f_labels = torch.randint(0, 64, (2, 19))
+    with torch.no_grad():
+        cl, fl = m(coarse_token_ids=coarse, fine_token_ids=fine)
+        (_, fl_a), (kv_a, emb_a) = m(coarse_token_ids=coarse, fine_token_ids=fine[:, :7], return_cache=True,
+                                     return_only_fine_logits=True)
+        (_, fl_b), _ = m(coarse_token_ids=coarse, fine_token_ids=fine[:, :8], return_cache=True, kv_cache=kv_a,
+                         embed_cache=emb_a, return_only_fine_logits=True)
+    m.zero_grad()
+    cl2, fl2 = m(coarse_token_ids=coarse, fine_token_ids=fine)
+    loss = ce(cl2, c_labels) + ce(fl2, f_labels)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    st = clone_state(m)
+    hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3, num_fine_quantizers=5)
+    (ocl, ofl), _ = ot.fine_forward(st, coarse, fine, **hk)
+    check("fine: coarse logits", ocl, cl)
+    check("fine: fine logits", ofl, fl)
+    (_, _), (okv_a, oemb_a) = ot.fine_forward(st, coarse, fine[:, :7], return_only_fine_logits=True, **hk)
+    (_, ofl_b), _ = ot.fine_forward(st, coarse, fine[:, :8], kv_cache=okv_a, embed_cache=oemb_a,
+                                    return_only_fine_logits=True, **hk)
+    check("fine cached step", ofl_b, fl_b)
+    check("fine loss", ce(ocl, c_labels) + ce(ofl, f_labels), loss.detach())
+    out["fine"] = dict(kwargs=kw, state=st, coarse=coarse, fine=fine, c_labels=c_labels, f_labels=f_labels,
+                       coarse_logits=cl, fine_logits=fl, fine_logits_b=fl_b, loss=loss.detach(), grads=grads)
+    torch.save(out, GOLDEN / "relpos.pt")
+
+
 def golden_sampling(ref):
     torch.manual_seed(51)
     logits = torch.randn(4, 65) * 3
@@ -286,6 +410,8 @@ def golden_soundstream(ref):
 
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    import random
+    random.seed(20240607)  # hyper-connections picks its initial stream with `random.randrange` (third_party.py:60)
     ref = ref_import.load()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -294,6 +420,7 @@ def main():
         golden_semantic_plain(ref)
         golden_coarse(ref)
         golden_fine(ref)
+        golden_relpos(ref)
         golden_sampling(ref)
         golden_soundstream(ref)
     total = sum(p.stat().st_size for p in GOLDEN.glob("*.pt"))

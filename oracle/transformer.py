@@ -97,6 +97,20 @@ def hyper_depth(branch_out, mixed, beta):
     return out.permute(0, 2, 1, 3).reshape(b * s, n, d)
 
 
+def rel_pos_bias(st, i, j):
+    """RelativePositionBias.forward (audiolm_pytorch.py:225-242): MLP over the offsets -(j-1)..(j-1), gathered
+    to [h, i, j] with queries right-aligned.  st holds net.{k}.0.{weight,bias} (SiLU layers) and the last Linear."""
+    n_layers = max(int(k.split(".")[1]) for k in st if k.startswith("net."))
+    x = torch.arange(-j + 1, j, device=st[f"net.{n_layers}.weight"].device).float()[:, None]
+    for k in range(n_layers):
+        x = F.silu(x @ st[f"net.{k}.0.weight"].t() + st[f"net.{k}.0.bias"])
+    x = x @ st[f"net.{n_layers}.weight"].t() + st[f"net.{n_layers}.bias"]
+    i_pos = torch.arange(i, device=x.device) + (j - i)
+    j_pos = torch.arange(j, device=x.device)
+    rel = i_pos[:, None] - j_pos[None, :] + (j - 1)
+    return x[rel].permute(2, 0, 1)
+
+
 def transformer(st, x, *, heads, depth, num_streams=4, self_attn_mask=None, attn_bias=None, kv_cache=None,
                 add_value_residual=True):
     """Transformer.forward without cross attention (audiolm_pytorch.py:461-560).
@@ -106,7 +120,10 @@ def transformer(st, x, *, heads, depth, num_streams=4, self_attn_mask=None, attn
     (grad_shrink is identity in forward, :93-94.)
     """
     cache_len = 0 if kv_cache is None else kv_cache.shape[-2]
+    n_full = x.shape[1]
     x = x[:, cache_len:]
+    if attn_bias is None and "rel_pos_bias.net.0.0.weight" in st:  # flash_attn=False models (:442, 503)
+        attn_bias = rel_pos_bias(sub(st, "rel_pos_bias"), n_full, n_full)
     if attn_bias is not None:
         attn_bias = attn_bias[..., cache_len:, :]
     if num_streams > 1:
@@ -180,8 +197,14 @@ def coarse_forward(st, semantic_ids, coarse_ids, *, heads, depth, codebook_size,
     S = sem.shape[1]
     x = torch.cat((st["semantic_start_token"].expand(b, 1, -1), sem,
                    st["coarse_start_token"].expand(b, 1, -1), coarse), dim=1)
+    attn_bias = None
+    if "cross_attn_bias" in st:  # :920-936: one learned scalar per head between the two segments
+        n_all = x.shape[1]
+        attn_bias = rel_pos_bias(sub(st, "transformer.rel_pos_bias"), n_all, n_all)
+        is_sem = torch.arange(n_all, device=dev) < S + 1
+        attn_bias = torch.where(is_sem[:, None] ^ is_sem[None, :], st["cross_attn_bias"], attn_bias)
     h, cache = transformer(sub(st, "transformer"), x, heads=heads, depth=depth, num_streams=num_streams,
-                           self_attn_mask=self_attn_mask, kv_cache=kv_cache)
+                           self_attn_mask=self_attn_mask, attn_bias=attn_bias, kv_cache=kv_cache)
     if embed_cache is not None:
         h = torch.cat((embed_cache, h), dim=-2)
     pred_sem, pred_coarse = h[:, :S], h[:, S + 1:]
@@ -189,6 +212,29 @@ def coarse_forward(st, semantic_ids, coarse_ids, *, heads, depth, codebook_size,
     if not return_only_coarse_logits and "to_semantic_logits.weight" in st:
         sem_logits = pred_sem @ st["to_semantic_logits.weight"].t() + st["to_semantic_logits.bias"]
     return (sem_logits, grouped_logits(st["coarse_logit_weights"], pred_coarse)), (cache, h)
+
+
+def fine_pos_bias(st, n, nf, qc, qf, dev):
+    """the engineered coarse/fine attention bias (audiolm_pytorch.py:1229-1298) -> [h, L, L], L = n + nf + 2."""
+    cs, fs = -(-n // qc), -(-nf // qf)
+    max_seq = max(cs, fs)
+    pos = torch.cat((torch.tensor([-1], device=dev), torch.arange(cs, device=dev).repeat_interleave(qc)[:n],
+                     torch.tensor([-1], device=dev), torch.arange(fs, device=dev).repeat_interleave(qf)[:nf]))
+    off = torch.cat((torch.tensor([0], device=dev), torch.arange(qc, device=dev).repeat(cs)[:n],
+                     torch.tensor([0], device=dev), torch.arange(qf, device=dev).repeat(fs)[:nf] + qc))
+    num_off = qc + qf
+    rel_seq, rel_off = 2 * max_seq - 1, 2 * num_off - 1
+    inp = torch.stack((torch.arange(rel_seq, device=dev).repeat_interleave(rel_off),
+                       torch.arange(rel_off, device=dev).repeat(rel_seq)), dim=-1).float()
+    t = F.silu(inp @ st["pos_bias_mlp.0.weight"].t() + st["pos_bias_mlp.0.bias"])
+    t = F.silu(t @ st["pos_bias_mlp.2.weight"].t() + st["pos_bias_mlp.2.bias"])
+    t = t @ st["pos_bias_mlp.4.weight"].t() + st["pos_bias_mlp.4.bias"]
+    pc = pos.clamp(min=0)
+    d_pos = pc[:, None] - pc[None, :] + max_seq - 1
+    d_off = off[:, None] - off[None, :] + num_off - 1
+    bias = t[d_pos * rel_off + d_off].permute(2, 0, 1)
+    start = pos == -1
+    return torch.where(start[:, None] | start[None, :], st["null_pos_bias"], bias)
 
 
 def fine_forward(st, coarse_ids, fine_ids, *, heads, depth, codebook_size, num_coarse_quantizers,
@@ -210,8 +256,11 @@ def fine_forward(st, coarse_ids, fine_ids, *, heads, depth, codebook_size, num_c
     fine = fine + st["fine_quantize_embedding.weight"][torch.arange(nf, device=dev) % qf]
     x = torch.cat((st["coarse_start_token"].expand(b, 1, -1), coarse,
                    st["fine_start_token"].expand(b, 1, -1), fine), dim=1)
+    attn_bias = None
+    if "pos_bias_mlp.0.weight" in st:
+        attn_bias = fine_pos_bias(st, n, nf, qc, qf, dev)
     h, cache = transformer(sub(st, "transformer"), x, heads=heads, depth=depth, num_streams=num_streams,
-                           self_attn_mask=self_attn_mask, kv_cache=kv_cache)
+                           self_attn_mask=self_attn_mask, attn_bias=attn_bias, kv_cache=kv_cache)
     if embed_cache is not None:
         h = torch.cat((embed_cache, h), dim=-2)
     pred_coarse, pred_fine = h[:, :n], h[:, n + 1:]

@@ -28,6 +28,36 @@ def test_state_dict_keys_match_reference(fixture, cls_name):
     m.load_state_dict(g["state"], strict=True)
 
 
+@pytest.mark.parametrize("which,cls_name", [("semantic", "SemanticTransformer"), ("coarse", "CoarseTransformer"),
+                                            ("fine", "FineTransformer")])
+def test_state_dict_keys_match_reference_rel_pos_bias(which, cls_name):
+    """flash_attn=False: rel_pos_bias.net.*, cross_attn_bias, pos_bias_mlp.*, null_pos_bias."""
+    from audiolm_pytorch_b200 import audiolm
+
+    g = load("relpos.pt")[which]
+    m = getattr(audiolm, cls_name)(**g["kwargs"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in g["state"].items()}
+    m.load_state_dict(g["state"], strict=True)
+
+
+def test_fine_pos_bias_index_matches_oracle():
+    """the int32 index map + MLP inputs the gather kernel consumes reproduce the oracle's dense bias."""
+    from audiolm_pytorch_b200 import audiolm
+    from oracle import transformer as ot
+
+    g = load("relpos.pt")["fine"]
+    m = audiolm.FineTransformer(**g["kwargs"])
+    m.load_state_dict(g["state"])
+    st = g["state"]
+    n, nf = 12, 18
+    idx, mlp_in = m._pos_bias_index(n, nf, "cpu")
+    t = torch.nn.functional.silu(mlp_in @ st["pos_bias_mlp.0.weight"].t() + st["pos_bias_mlp.0.bias"])
+    t = torch.nn.functional.silu(t @ st["pos_bias_mlp.2.weight"].t() + st["pos_bias_mlp.2.bias"])
+    t = t @ st["pos_bias_mlp.4.weight"].t() + st["pos_bias_mlp.4.bias"]
+    dense = torch.where((idx < 0)[None], st["null_pos_bias"], t[idx.clamp(min=0).long()].permute(2, 0, 1))
+    assert torch.allclose(dense, ot.fine_pos_bias(st, n, nf, 3, 5, "cpu"), atol=1e-6)
+
+
 def test_c_abi_exports_every_declared_symbol():
     lib_path = ROOT / "audiolm_pytorch_b200" / "libalm_b200.so"
     if not lib_path.exists():

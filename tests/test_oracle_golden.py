@@ -129,3 +129,56 @@ def test_causal_conv_transpose(s):
     y = oc.causal_conv_transpose1d(c["x"], c["w"], c["b"], s)
     assert y.shape[-1] == c["x"].shape[-1] * s
     assert close(y, c["y"], 1e-5)
+
+
+def test_relative_position_bias_models():
+    """flash_attn=False models: RelativePositionBias / cross_attn_bias / pos_bias_mlp."""
+    import torch.nn.functional as F
+
+    g = load("relpos.pt")
+
+    def ce(lg, lb):
+        return F.cross_entropy(lg.transpose(1, 2), lb)
+
+    s = g["semantic"]
+    hk = dict(heads=2, depth=2)
+    lg, _ = ot.semantic_forward(s["state"], s["ids"], **hk)
+    assert close(lg, s["logits"])
+    assert close(ot.semantic_forward(s["state"], s["ids"], self_attn_mask=s["mask"], **hk)[0], s["logits_masked"])
+    _, c12 = ot.semantic_forward(s["state"], s["ids"][:, :12], **hk)
+    assert close(ot.semantic_forward(s["state"], s["ids"][:, :13], kv_cache=c12, **hk)[0], s["logits_inc"])
+    assert close(ce(lg, s["labels"]), s["loss"], 1e-5)
+
+    c = g["coarse"]
+    hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3)
+    (sl, cl), _ = ot.coarse_forward(c["state"], c["sem"], c["coarse"], **hk)
+    assert close(sl, c["sem_logits"]) and close(cl, c["coarse_logits"])
+    _, (kv_a, emb_a) = ot.coarse_forward(c["state"], c["sem"], c["coarse"][:, :9], return_only_coarse_logits=True, **hk)
+    (_, cl_b), _ = ot.coarse_forward(c["state"], c["sem"], c["coarse"][:, :10], kv_cache=kv_a, embed_cache=emb_a,
+                                     return_only_coarse_logits=True, **hk)
+    assert close(cl_b, c["coarse_logits_b"])
+
+    f = g["fine"]
+    hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3, num_fine_quantizers=5)
+    (cl, fl), _ = ot.fine_forward(f["state"], f["coarse"], f["fine"], **hk)
+    assert close(cl, f["coarse_logits"]) and close(fl, f["fine_logits"])
+    _, (kv_a, emb_a) = ot.fine_forward(f["state"], f["coarse"], f["fine"][:, :7], return_only_fine_logits=True, **hk)
+    (_, fl_b), _ = ot.fine_forward(f["state"], f["coarse"], f["fine"][:, :8], kv_cache=kv_a, embed_cache=emb_a,
+                                   return_only_fine_logits=True, **hk)
+    assert close(fl_b, f["fine_logits_b"])
+    assert close(ce(cl, f["c_labels"]) + ce(fl, f["f_labels"]), f["loss"], 1e-5)
+
+
+def test_relative_position_bias_grads():
+    """oracle autograd reproduces the reference's gradients of the bias parameters."""
+    import torch.nn.functional as F
+
+    g = load("relpos.pt")["coarse"]
+    st = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state"].items()}
+    (sl, cl), _ = ot.coarse_forward(st, g["sem"], g["coarse"], heads=2, depth=2, codebook_size=64,
+                                    num_coarse_quantizers=3)
+    loss = F.cross_entropy(sl.transpose(1, 2), g["sem_labels"]) + F.cross_entropy(cl.transpose(1, 2), g["coarse_labels"])
+    loss.backward()
+    for k in ("cross_attn_bias", "transformer.rel_pos_bias.net.0.0.weight", "transformer.rel_pos_bias.net.2.0.weight",
+              "transformer.rel_pos_bias.net.3.bias"):
+        assert close(st[k].grad, g["grads"][k], 1e-3), k
