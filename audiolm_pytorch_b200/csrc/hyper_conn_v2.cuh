@@ -14,7 +14,7 @@ namespace hc2 {
 
 constexpr int S = 4, T = 5;
 constexpr int THREADS = 256;      // a CTA holds THREADS / TPT token slots; TPT = threads per token (64 or 128)
-constexpr int AUX = S * T + S + S + 2;
+constexpr int AUX = S * T + S + S + (S * T + S) + 2;  // ta[20] tb[4] inv[4] z[24] (pre-tanh) mean rstd
 
 template <int TPT>
 __device__ __forceinline__ void bar_slot(int id) {
@@ -214,6 +214,11 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
       }
     }
     slot_sum<S * T + S, TPT>(w, mail, which, w2, lane, bar_id);
+    if (lt == 0) {  // pre-activations: the backward's RMS-norm term needs them (hyper_conn_v3.cuh)
+      float* az = aux + (size_t)m * AUX + S * T + S + S;
+#pragma unroll
+      for (int i = 0; i < S * T + S; ++i) az[i] = w[i];
+    }
     float alpha[S][T], beta[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {

@@ -36,9 +36,13 @@ def profile_stop():
     return out
 
 
+CLASS_UNIT = {}  # kernel class -> "flop" (tensor-bound classes) or "byte" (HBM-bound classes: algorithmic bytes)
+
+
 class _timed:
-    def __init__(self, cls, work):
+    def __init__(self, cls, work, unit="flop"):
         self.cls, self.work = cls, work
+        CLASS_UNIT[cls] = unit
 
     def __enter__(self):
         if _PROFILE is not None:
@@ -61,7 +65,7 @@ def _check_cuda(*ts):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, alpha=1.0, bias=None,
-         acc_mode=0, split_k=1):
+         acc_mode=0, split_k=1, cls="gemm_bf16_tcgen05"):
     """out[b,m,n] (op)= alpha * sum_k A(m,k) B(n,k) (+bias[n]).   bf16 operands, fp32 accumulate.
 
     a: [(batch,) M, K] (a_mn=False) or [(batch,) K, M] (a_mn=True); row stride must be a multiple of 8.
@@ -95,7 +99,6 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, alpha=1.0, b
     assert o3.dtype in (bf16, f32)
     if bias is not None:
         assert bias.dtype == f32 and bias.numel() == N and bias.is_contiguous()
-    cls = "gemm_bf16_tcgen05"
     if _PROFILE is not None and PROFILE_SHAPES:
         cls += f" M{M} N{N} K{K} b{nb} {'mn' if a_mn else 'k'}{'mn' if b_mn else 'k'} s{split_k}"
     with _timed(cls, 2.0 * M * N * K * nb):
@@ -212,7 +215,8 @@ def bias_gather_bwd(dbias, idx, table_rows, *, want_override):
     return dtable, dover
 
 
-HC_AUX = 30  # floats of per-token state kept for the backward (see csrc/hyper_conn.cu)
+HC_BWD_SPLIT = True  # False: hc2 kernel with in-kernel parameter-gradient accumulators (kept for A/B tests)
+HC_AUX = 54  # floats of per-token state kept for the backward (see csrc/hyper_conn.cu)
 
 
 def _hc_param_ptrs(hc, ln_gamma):
@@ -231,8 +235,9 @@ def hc_pre_fwd(hc, ln_gamma, *, R_in=None, Y=None, beta_prev=None, x_expand=None
     xn = torch.empty(M, d, device=dev, dtype=bf16)
     beta = torch.empty(M, streams, device=dev, dtype=f32)
     aux = torch.empty(M, HC_AUX, device=dev, dtype=f32)
-    _lib.call("alm_hc_pre_fwd", R_in, Y, beta_prev, x_expand, *_hc_param_ptrs(hc, ln_gamma),
-              R_out, bin_, xn, beta, aux, M, d, streams)
+    with _timed("hc_pre_fwd", M * d * ((4 if x_expand is not None else 10) + 12), "byte"):
+        _lib.call("alm_hc_pre_fwd", R_in, Y, beta_prev, x_expand, *_hc_param_ptrs(hc, ln_gamma),
+                  R_out, bin_, xn, beta, aux, M, d, streams)
     return R_out, bin_, xn, beta, aux
 
 
@@ -251,10 +256,26 @@ def hc_pre_bwd(hc, ln_gamma, grads, g_ln_gamma, aux, dR_out, dxn, dbeta, *, dbin
         dR_in = torch.empty(M, streams, d, device=dev, dtype=bf16)
         dY = torch.empty(M, d, device=dev, dtype=bf16)
         dbp = torch.empty(M, streams, device=dev, dtype=f32)
-    _lib.call("alm_hc_pre_bwd", R_in, Y, beta_prev, x_expand, *_hc_param_ptrs(hc, ln_gamma), aux, dR_out, dxn,
-              dbin_extra, dbeta, dR_in, dY, dbp, dx, float(dx_scale),
-              grads["gamma"], grads["dyn_alpha"], grads["dyn_beta"], grads["static_alpha"], grads["static_beta"],
-              grads["alpha_scale"], grads["beta_scale"], g_ln_gamma, M, d, streams)
+    # hc3 path: per-channel parameter gradients via two skinny tcgen05 GEMMs instead of in-kernel accumulators
+    split = x_expand is None and d <= 1024 and HC_BWD_SPLIT
+    w = torch.empty(M * streams, 8, device=dev, dtype=bf16) if split else None
+    wy = torch.empty(M, 8, device=dev, dtype=bf16) if split else None
+    nbytes = M * d * ((4 + 8 + 2 + 4 if x_expand is not None else 8 + 2 + 8 + 2 + 8 + 2) + (2 if dbin_extra is not None else 0))
+    with _timed("hc_pre_bwd", nbytes, "byte"):
+        _lib.call("alm_hc_pre_bwd", R_in, Y, beta_prev, x_expand, *_hc_param_ptrs(hc, ln_gamma), aux, dR_out, dxn,
+                  dbin_extra, dbeta, dR_in, dY, dbp, dx, float(dx_scale),
+                  grads["gamma"], grads["dyn_alpha"], grads["dyn_beta"], grads["static_alpha"], grads["static_beta"],
+                  grads["alpha_scale"], grads["beta_scale"], g_ln_gamma, w, wy, M, d, streams)
+    if split:
+        G = torch.zeros(d, 8, device=dev, dtype=f32)
+        rows = M * streams
+        sk = max(1, min(64, (rows // 64) // 8, 2 * 148 // max(1, (d + 127) // 128)))
+        # (HBM-bound: they stream R_in / Y once; kept out of the tensor-bound GEMM class of the roofline)
+        gemm(R_in.view(rows, d), w, a_mn=True, b_mn=True, out=G, acc_mode=2, split_k=sk, cls="gemm_skinny_hc_param_grad")
+        sk = max(1, min(64, (M // 64) // 8, 2 * 148 // max(1, (d + 127) // 128)))
+        gemm(Y, wy, a_mn=True, b_mn=True, out=G, acc_mode=2, split_k=sk, cls="gemm_skinny_hc_param_grad")
+        _lib.call("alm_hc_param_finish", G, hc["gamma"], hc["dyn_alpha"], hc["dyn_beta"], grads["gamma"],
+                  grads["dyn_alpha"], grads["dyn_beta"], d)
     return dx if x_expand is not None else (dR_in, dY, dbp)
 
 
@@ -278,7 +299,8 @@ def geglu_ln_fwd(h, gamma, *, inner, inner_pad):
     M = h.shape[0]
     gn = torch.empty(M, inner_pad, device=h.device, dtype=bf16)
     stats = torch.empty(M, 2, device=h.device, dtype=f32)
-    _lib.call("alm_geglu_ln_fwd", h, h.stride(0), inner_pad, gamma, gn, gn.stride(0), stats, M, inner, inner_pad)
+    with _timed("geglu_ln_fwd", M * inner_pad * 6, "byte"):
+        _lib.call("alm_geglu_ln_fwd", h, h.stride(0), inner_pad, gamma, gn, gn.stride(0), stats, M, inner, inner_pad)
     return gn, stats
 
 
@@ -286,8 +308,9 @@ def geglu_ln_bwd(h, gamma, stats, dgn, g_gamma, *, inner, inner_pad):
     M = h.shape[0]
     dh = torch.empty_like(h)
     assert dh.stride(0) == h.stride(0)
-    _lib.call("alm_geglu_ln_bwd", h, h.stride(0), inner_pad, gamma, stats, dgn, dgn.stride(0), dh, g_gamma, M,
-              inner, inner_pad)
+    with _timed("geglu_ln_bwd", M * inner_pad * 10, "byte"):
+        _lib.call("alm_geglu_ln_bwd", h, h.stride(0), inner_pad, gamma, stats, dgn, dgn.stride(0), dh, g_gamma, M,
+                  inner, inner_pad)
     return dh
 
 

@@ -292,7 +292,12 @@ def main_ours(args):
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     kern = {}
     for cls, (ms_, work, n_) in prof.items():
-        kern[cls] = {"ms_per_step": ms_ / 2, "launches_per_step": n_ / 2, "tflops": work / (ms_ * 1e-3) / 1e12 if ms_ else 0}
+        rate = work / (ms_ * 1e-3) if ms_ else 0.0
+        kern[cls] = {"ms_per_step": ms_ / 2, "launches_per_step": n_ / 2}
+        if ops.CLASS_UNIT.get(cls) == "byte":  # HBM-bound classes: algorithmic bytes / time vs the measured copy peak
+            kern[cls].update(gbps=rate / 1e9, frac_of_hbm_peak=rate / 1e9 / pk["hbm"] if pk.get("hbm") else None)
+        else:
+            kern[cls]["tflops"] = rate / 1e12
 
     line = {
         "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
