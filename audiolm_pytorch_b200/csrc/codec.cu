@@ -6,7 +6,10 @@
 // These are CUDA-core kernels: the convs and the code search are FMA-bound in fp32 (arithmetic
 // intensity 64-512 FLOP/B); data movement is coalesced along time and staged through
 // shared memory so each input sample / codebook row is read from HBM once per output tile.
+#include <stdlib.h>
+
 #include "alm_common.cuh"
+#include "conv_tiled.cuh"
 
 namespace alm {
 
@@ -269,6 +272,161 @@ rvq_encode_kernel(const float* __restrict__ x, long long ldx, const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// residual VQ, second generation: same arithmetic (dot products accumulate over d in ascending order with one fp32
+// FMA chain, so every distance - and therefore every index - is bit-identical to rvq_encode_kernel above), but
+//   * a thread owns 8 rows x 4 codes (32 accumulators): per 4 channels it issues 8 broadcast LDS.128 (rows) and
+//     4 conflict-free LDS.128 (codes) for 128 FMAs - the first version issued 4 LDS.128 per 16 FMAs and ran at 4 %
+//     of the FMA peak, stalled on shared-memory bandwidth and on synchronous codebook loads
+//     (profiles/r01_ncu_rvq_v1.csv: issue active 16 %, long_scoreboard 402k samples);
+//   * the codebook streams through shared memory in [256 codes x 32 channels] chunks with cp.async double buffering.
+// CTA = 32 rows (4 row groups x 8) x 256 codes per tile (2 code groups x 32 lanes x 4), all Q stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int RQ_ROWS = 32, RQ_CT = 256, RQ_KC = 32, RQ_ES = RQ_KC + 4, RQ_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;  // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(RQ_THREADS, 1)
+rvq_encode_v2_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ cb,
+                     const float* __restrict__ e2, float* __restrict__ quant, long long ldq,
+                     long long* __restrict__ indices, long long ldi, int N, int D, int C, int Q) {
+  extern __shared__ __align__(16) float smem[];
+  const int DP = D + 4;
+  float* R = smem;                                 // [RQ_ROWS][DP] residual
+  float* E = R + RQ_ROWS * DP;                     // [2][RQ_CT][RQ_ES] codebook chunk (double buffered)
+  float* x2 = E + 2 * RQ_CT * RQ_ES;               // [RQ_ROWS]
+  float* sbd = x2 + RQ_ROWS;                       // [2][RQ_ROWS] best distance per code group
+  int* sbi = reinterpret_cast<int*>(sbd + 2 * RQ_ROWS);  // [2][RQ_ROWS]
+  int* best_idx = sbi + 2 * RQ_ROWS;               // [RQ_ROWS]
+  const int n0 = blockIdx.x * RQ_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rg = warp & 3, cg = warp >> 2;         // row group (8 rows), code group (128 codes of the tile)
+  const int n_kc = D / RQ_KC;
+  for (int i = tid; i < RQ_ROWS * D; i += RQ_THREADS) {
+    const int r = i / D, d = i - r * D;
+    R[r * DP + d] = (n0 + r < N) ? x[(size_t)(n0 + r) * ldx + d] : 0.f;
+  }
+  __syncthreads();
+  for (int q = 0; q < Q; ++q) {
+    {  // |r|^2 per row: 8 threads per row (same partial-sum order as the first-generation kernel)
+      const int r = tid >> 3, part = tid & 7;
+      float a = 0.f;
+      for (int d = part; d < D; d += 8) a = fmaf(R[r * DP + d], R[r * DP + d], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      if (part == 0) x2[r] = a;
+    }
+    float bd[8];
+    int bi[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) { bd[rr] = INFINITY; bi[rr] = 0; }
+    const float* cbq = cb + (size_t)q * C * D;
+    auto issue_chunk = [&](int c0, int kc, int buf) {
+      // 256 codes x 32 channels = 2048 float4: 8 per thread; a warp copies 4 codes x 128 B per pass (coalesced)
+      float* dst = E + buf * (RQ_CT * RQ_ES);
+#pragma unroll
+      for (int it = 0; it < (RQ_CT * RQ_KC / 4) / RQ_THREADS; ++it) {
+        const int v = tid + it * RQ_THREADS;
+        const int code = v >> 3, f4 = v & 7;
+        const bool ok = c0 + code < C;
+        cp_async16(dst + code * RQ_ES + f4 * 4, cbq + (size_t)(ok ? c0 + code : 0) * D + kc * RQ_KC + f4 * 4, ok);
+      }
+      cp_async_commit();
+    };
+    for (int c0 = 0; c0 < C; c0 += RQ_CT) {
+      float acc[8][4];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) acc[rr][cc] = 0.f;
+      __syncthreads();  // every warp is done with both chunk buffers (and x2 / R are up to date)
+      issue_chunk(c0, 0, 0);
+      for (int kc = 0; kc < n_kc; ++kc) {
+        if (kc + 1 < n_kc) {
+          issue_chunk(c0, kc + 1, (kc + 1) & 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* rbase = R + (rg * 8) * DP + kc * RQ_KC;
+        const float* ebase = E + (kc & 1) * (RQ_CT * RQ_ES) + (cg * 128 + lane) * RQ_ES;
+#pragma unroll 2
+        for (int d4 = 0; d4 < RQ_KC / 4; ++d4) {
+          float4 ev[4];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) ev[cc] = *reinterpret_cast<const float4*>(ebase + cc * 32 * RQ_ES + d4 * 4);
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const float4 rv = *reinterpret_cast<const float4*>(rbase + rr * DP + d4 * 4);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              float a = acc[rr][cc];
+              a = fmaf(rv.x, ev[cc].x, a);
+              a = fmaf(rv.y, ev[cc].y, a);
+              a = fmaf(rv.z, ev[cc].z, a);
+              a = fmaf(rv.w, ev[cc].w, a);
+              acc[rr][cc] = a;
+            }
+          }
+        }
+        __syncthreads();  // this chunk buffer may be refilled by the copy issued in the next iteration
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // codes in increasing order per thread: strict '<' keeps the lowest index
+        const int c = c0 + cg * 128 + lane + 32 * cc;
+        if (c < C) {
+          const float e2c = e2[(size_t)q * C + c];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const float d2 = (x2[rg * 8 + rr] + e2c) + (-2.f * acc[rr][cc]);
+            const float dist = __fsqrt_rn(fmaxf(d2, 0.f));
+            if (dist < bd[rr]) { bd[rr] = dist; bi[rr] = c; }
+          }
+        }
+      }
+    }
+    // argmin across the 32 lanes, then across the two code groups (lowest index wins ties)
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd[rr], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi[rr], o);
+        if (od < bd[rr] || (od == bd[rr] && oi < bi[rr])) { bd[rr] = od; bi[rr] = oi; }
+      }
+      if (lane == 0) { sbd[cg * RQ_ROWS + rg * 8 + rr] = bd[rr]; sbi[cg * RQ_ROWS + rg * 8 + rr] = bi[rr]; }
+    }
+    __syncthreads();
+    if (tid < RQ_ROWS) {
+      const float d0 = sbd[tid], d1 = sbd[RQ_ROWS + tid];
+      const int i0 = sbi[tid], i1 = sbi[RQ_ROWS + tid];
+      best_idx[tid] = (d1 < d0 || (d1 == d0 && i1 < i0)) ? i1 : i0;
+    }
+    __syncthreads();
+    // residual -= code ; quantized += code ; emit index
+    for (int i = tid; i < RQ_ROWS * D; i += RQ_THREADS) {
+      const int r = i / D, d = i - r * D;
+      if (n0 + r < N) {
+        const float e = cbq[(size_t)best_idx[r] * D + d];
+        R[r * DP + d] -= e;
+        float* qp = quant + (size_t)(n0 + r) * ldq + d;
+        *qp = (q == 0 ? 0.f : *qp) + e;
+      }
+    }
+    if (tid < RQ_ROWS && n0 + tid < N) indices[(size_t)(n0 + tid) * ldi + q] = best_idx[tid];
+    __syncthreads();
+  }
+}
+
 // out[n, :] = sum_q cb[q][idx[n, q]]   (idx < 0 = dropped quantizer -> contributes 0)
 __global__ void rvq_decode_kernel(const long long* __restrict__ indices, long long ldi, const float* __restrict__ cb,
                                   float* __restrict__ out, long long ldo, int N, int D, int C, int Q) {
@@ -289,7 +447,7 @@ using namespace alm;
 
 extern "C" int alm_causal_conv1d_fwd(const float* x, const float* w, const float* bias, const float* residual,
                                      float* y, int B, int Cin, int Cout, int T, int K, int stride, int dilation,
-                                     int pad_mode, int act_elu, alm_stream_t stream_) {
+                                     int pad_mode, int act_elu, int w_packed, alm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(x && w && y && B > 0 && Cin > 0 && Cout > 0 && T > 0 && K > 0 && stride > 0 && dilation > 0,
               ALM_ERR_ARG);
@@ -298,6 +456,15 @@ extern "C" int alm_causal_conv1d_fwd(const float* x, const float* w, const float
   ALM_REQUIRE(pad >= 0, ALM_ERR_ARG);
   ALM_REQUIRE(pad_mode != 0 || pad < T, ALM_ERR_ARG);  // reflect needs pad < T (as F.pad does)
   const int Tout = (T + pad - dilation * (K - 1) - 1) / stride + 1;
+  {
+    static const bool tiled = getenv("ALM_CONV_V1") == nullptr;  // A/B switch: first-generation kernel
+    if (tiled || w_packed) {
+      const int rc = cvt::dispatch(x, w, bias, residual, y, B, Cin, Cout, T, Tout, K, stride, dilation, pad, pad_mode,
+                                   act_elu, w_packed, stream);
+      if (rc != -1) return rc;
+    }
+  }
+  ALM_REQUIRE(!w_packed, ALM_ERR_UNSUPPORTED);  // the generic kernel reads the torch layout only
   const int span = (CV_T - 1) * stride + (K - 1) * dilation + 1;
   const size_t smem = (size_t)(CV_CI * span + CV_CI * K * CV_CO) * sizeof(float);
   ALM_REQUIRE(smem <= 200 * 1024, ALM_ERR_UNSUPPORTED);
@@ -335,6 +502,23 @@ extern "C" int alm_rvq_encode(const float* x, int64_t ldx, const float* codebook
   ALM_REQUIRE(ldx % 4 == 0 || true, ALM_ERR_ALIGN);
   code_norms_kernel<<<ceil_div(Q * C * 32, 256), 256, 0, stream>>>(codebooks, e2_workspace, Q * C, D);
   ALM_CHECK_LAUNCH();
+  static const bool rvq_v1 = getenv("ALM_RVQ_V1") != nullptr;  // A/B switch
+  if (!rvq_v1 && D % RQ_KC == 0 && ((reinterpret_cast<uintptr_t>(codebooks) & 15u) == 0)) {
+    const size_t smem2 = (size_t)(RQ_ROWS * (D + 4) + 2 * RQ_CT * RQ_ES + RQ_ROWS + 2 * RQ_ROWS) * sizeof(float) +
+                         (size_t)(2 * RQ_ROWS + RQ_ROWS) * sizeof(int);
+    if (smem2 <= 200 * 1024) {
+      static size_t attr2 = 0;
+      if (smem2 > attr2) {
+        ALM_CUDA_OK(cudaFuncSetAttribute(rvq_encode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr2 = smem2;
+      }
+      rvq_encode_v2_kernel<<<ceil_div(N, RQ_ROWS), RQ_THREADS, smem2, stream>>>(
+          x, ldx, codebooks, e2_workspace, quantized, ldq, reinterpret_cast<long long*>(indices), ldi, N, D, C, Q);
+      ALM_CHECK_LAUNCH();
+      ALM_LAUNCHED(2);
+      return ALM_OK;
+    }
+  }
   const size_t smem = (size_t)((RV_ROWS + RV_CODES) * (D + 4) + 2 * RV_ROWS) * sizeof(float);
   ALM_REQUIRE(smem <= 200 * 1024, ALM_ERR_UNSUPPORTED);
   static size_t attr = 0;

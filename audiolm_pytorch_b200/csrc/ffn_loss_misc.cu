@@ -5,6 +5,8 @@
 //   attn_delta : rowsum(dO * O) for the attention backward
 //   axpby      : value-residual mix v = 0.5 (v + v_first) (audiolm_pytorch.py:355-358) and its backward
 //   cast_pad   : fp32 master weights -> zero-padded bf16 operand copies for the TMA/UMMA GEMMs
+#include <stdlib.h>
+
 #include "alm_common.cuh"
 
 namespace alm {
@@ -44,7 +46,46 @@ __device__ __forceinline__ void block_sum256(float (&v)[N], float* buf /*[N][8]*
   }
 }
 
+template <int N, int NT>
+__device__ __forceinline__ void block_sum_nt(float (&v)[N], float* buf /*[N][NT/32]*/) {
+  constexpr int NW = NT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();  // protect buf from the previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) buf[i * NW + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += buf[i * NW + w];
+    v[i] = s;
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+
+// Phi(x) = 0.5 (1 + erf(x / sqrt2)) and x * phi(x) for the erf GELU (audiolm_pytorch.py:246-249: F.gelu default)
+// with ONE exponential: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two orders below the bf16 outputs'
+// rounding), whose exp(-(x/sqrt2)^2) is also the Gaussian density.  ~14 instructions vs ~35 for erff + __expf.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& xpdf) {
+  const float ax = fabsf(x) * 0.7071067811865476f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float e;
+  const float arg = -0.7213475204444817f * x * x;  // -x^2/2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float half_tail = 0.5f * p * t * e;          // 0.5 * (1 - erf(|x|/sqrt2))
+  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+  xpdf = 0.3989422804014327f * x * e;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -52,60 +93,84 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // h [M, ldh]: a = h[:, 0:inner], gate = h[:, gate_off : gate_off+inner]   ->  gn [M, ldg] (cols >= inner are 0)
-template <int NCH>
-__global__ void __launch_bounds__(FF_THREADS)
+template <int NCH, int NT>
+__global__ void __launch_bounds__(NT)
 geglu_ln_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate_off,
                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ gn, long long ldg,
                     float* __restrict__ stats, int M, int inner, int inner_pad) {
-  __shared__ float buf[2 * 8];
+  __shared__ float buf[2 * (NT / 32)];
+  // software pipeline: the NEXT row's operands are loaded into registers before this row is reduced, so the
+  // load latency overlaps the erf / reduction / store phases of the current row (the row after that is pulled
+  // towards L2)
+  uint4 pa[NCH], pgt[NCH];
+  auto load_row = [&](int row, uint4* xa, uint4* xg) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c0 = (threadIdx.x + k * NT) * 8;
+      if (c0 < inner_pad) {
+        xa[k] = *reinterpret_cast<const uint4*>(h + (size_t)row * ldh + c0);
+        xg[k] = *reinterpret_cast<const uint4*>(h + (size_t)row * ldh + gate_off + c0);
+      }
+    }
+  };
+  if ((int)blockIdx.x < M) load_row(blockIdx.x, pa, pgt);
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
-    if (m + (int)gridDim.x < M && (threadIdx.x & 7) == 0) {  // L2 prefetch of this CTA's next row
+    uint4 na[NCH], ngt[NCH];
+    if (m + (int)gridDim.x < M) load_row(m + gridDim.x, na, ngt);
+    if (m + 2 * (int)gridDim.x < M && (threadIdx.x & 7) == 0) {  // L2 prefetch of the row after next
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
-        const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+        const int c0 = (threadIdx.x + k * NT) * 8;
         if (c0 < inner_pad) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + c0));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + gate_off + c0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + 2 * gridDim.x) * ldh + c0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + 2 * gridDim.x) * ldh + gate_off + c0));
         }
       }
     }
     float g[NCH][8];
-    float s1[1] = {0.f};
+    float s12[2] = {0.f, 0.f};  // sum, sum of squares: one block reduction per row
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+      const int c0 = (threadIdx.x + k * NT) * 8;
 #pragma unroll
       for (int e = 0; e < 8; ++e) g[k][e] = 0.f;
       if (c0 < inner_pad) {
         float a[8], gt[8];
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a);
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt);
+        unpack8b(pa[k], a);
+        unpack8b(pgt[k], gt);
+        const int nv = min(8, inner - c0);  // 8 except in the row's last (padded) chunk
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          g[k][e] = (c0 + e < inner) ? gelu_erf(gt[e]) * a[e] : 0.f;
-          s1[0] += g[k][e];
+          float cdf, xpdf;
+          gelu_parts(gt[e], cdf, xpdf);
+          const float v = e < nv ? gt[e] * cdf * a[e] : 0.f;
+          g[k][e] = v;
+          s12[0] += v;
+          s12[1] = fmaf(v, v, s12[1]);
         }
       }
     }
-    block_sum256<1>(s1, buf);
-    const float mean = s1[0] / inner;
-    float s2[1] = {0.f};
+    block_sum_nt<2, NT>(s12, buf);
+    const float mean = s12[0] / inner;
+    const float rstd = rsqrtf(fmaxf(s12[1] / inner - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (c0 + e < inner) s2[0] += (g[k][e] - mean) * (g[k][e] - mean);
-    }
-    block_sum256<1>(s2, buf);
-    const float rstd = rsqrtf(s2[0] / inner + 1e-5f);
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+      const int c0 = (threadIdx.x + k * NT) * 8;
       if (c0 < inner_pad) {
+        const int nv = min(8, inner - c0);
+        float gm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (nv == 8) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+          gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < nv) gm[e] = __ldg(gamma + c0 + e);
+        }
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (c0 + e < inner) ? (g[k][e] - mean) * rstd * gamma[c0 + e] : 0.f;
+        for (int e = 0; e < 8; ++e) o[e] = e < nv ? (g[k][e] - mean) * rstd * gm[e] : 0.f;
         *reinterpret_cast<uint4*>(gn + (size_t)m * ldg + c0) = pack8b(o);
       }
     }
@@ -113,16 +178,18 @@ geglu_ln_fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
       stats[(size_t)m * 2] = mean;
       stats[(size_t)m * 2 + 1] = rstd;
     }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) { pa[k] = na[k]; pgt[k] = ngt[k]; }
   }
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(FF_THREADS)
+template <int NCH, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
 geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate_off,
                     const float* __restrict__ gamma, const float* __restrict__ stats,
                     const __nv_bfloat16* __restrict__ dgn, long long ldg, __nv_bfloat16* __restrict__ dh,
                     float* __restrict__ g_gamma, int M, int inner, int inner_pad) {
-  __shared__ float buf[2 * 8];
+  __shared__ float buf[2 * (NT / 32)];
   float gacc[NCH][8];
 #pragma unroll
   for (int k = 0; k < NCH; ++k)
@@ -132,7 +199,7 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
     if (m + (int)gridDim.x < M && (threadIdx.x & 7) == 0) {  // L2 prefetch of this CTA's next row
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
-        const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+        const int c0 = (threadIdx.x + k * NT) * 8;
         if (c0 < inner_pad) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + c0));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(h + (size_t)(m + gridDim.x) * ldh + gate_off + c0));
@@ -141,53 +208,60 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
       }
     }
     const float mean = stats[(size_t)m * 2], rstd = stats[(size_t)m * 2 + 1];
-    // one erf per element: ge = gelu(gate) is kept; Phi(gate) = ge / gate is recovered from it in the second phase
-    float a[NCH][8], gt[NCH][8], gl[NCH][8], ge[NCH][8];
+    // phase 1 keeps per element: a, ge = gelu(gate), gp = gelu'(gate) and gl = dgn * gamma (one exponential each)
+    float a[NCH][8], gp[NCH][8], gl[NCH][8], ge[NCH][8];
     float r2[2] = {0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+      const int c0 = (threadIdx.x + k * NT) * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { a[k][e] = gt[k][e] = gl[k][e] = ge[k][e] = 0.f; }
+      for (int e = 0; e < 8; ++e) { a[k][e] = gp[k][e] = gl[k][e] = ge[k][e] = 0.f; }
       if (c0 < inner_pad) {
-        float dv[8];
+        float dv[8], gt[8];
         unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a[k]);
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt[k]);
+        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt);
         unpack8b(*reinterpret_cast<const uint4*>(dgn + (size_t)m * ldg + c0), dv);
+        const int nv = min(8, inner - c0);
+        float gm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (nv == 8) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+          gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < nv) gm[e] = __ldg(gamma + c0 + e);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          if (c0 + e < inner) {
-            ge[k][e] = gelu_erf(gt[k][e]);
-            const float xh = (ge[k][e] * a[k][e] - mean) * rstd;
-            gl[k][e] = dv[e] * gamma[c0 + e];
-            gacc[k][e] += dv[e] * xh;
-            r2[0] += gl[k][e];
-            r2[1] += gl[k][e] * xh;
-          }
+          float cdf, xpdf;
+          gelu_parts(gt[e], cdf, xpdf);
+          const bool ok = e < nv;
+          ge[k][e] = ok ? gt[e] * cdf : 0.f;
+          gp[k][e] = ok ? cdf + xpdf : 0.f;
+          if (!ok) { a[k][e] = 0.f; dv[e] = 0.f; }
+          const float xh = (ge[k][e] * a[k][e] - mean) * rstd;
+          gl[k][e] = dv[e] * gm[e];
+          gacc[k][e] = fmaf(dv[e], xh, gacc[k][e]);
+          r2[0] += gl[k][e];
+          r2[1] = fmaf(gl[k][e], xh, r2[1]);
         }
       }
     }
-    block_sum256<2>(r2, buf);
+    block_sum_nt<2, NT>(r2, buf);
     const float m1 = r2[0] / inner, m2 = r2[1] / inner;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+      const int c0 = (threadIdx.x + k * NT) * 8;
       if (c0 < inner_pad) {
+        const int nv = min(8, inner - c0);
         float da[8], dg8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          if (c0 + e < inner) {
-            const float x = gt[k][e];
-            const float xh = (ge[k][e] * a[k][e] - mean) * rstd;
-            const float dg = rstd * (gl[k][e] - m1 - xh * m2);
-            // Phi(x) = gelu(x)/x (series 0.5 + x*phi(0) near 0);  gelu'(x) = Phi(x) + x*phi(x)
-            const float cdf = fabsf(x) > 1e-3f ? __fdividef(ge[k][e], x) : fmaf(x, 0.3989422804014327f, 0.5f);
-            const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-            da[e] = dg * ge[k][e];
-            dg8[e] = dg * a[k][e] * fmaf(x, pdf, cdf);
-          } else {
-            da[e] = dg8[e] = 0.f;
-          }
+          const float xh = (ge[k][e] * a[k][e] - mean) * rstd;
+          const float dg = e < nv ? rstd * (gl[k][e] - m1 - xh * m2) : 0.f;
+          da[e] = dg * ge[k][e];
+          dg8[e] = dg * a[k][e] * gp[k][e];
         }
         *reinterpret_cast<uint4*>(dh + (size_t)m * ldh + c0) = pack8b(da);
         *reinterpret_cast<uint4*>(dh + (size_t)m * ldh + gate_off + c0) = pack8b(dg8);
@@ -196,7 +270,7 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
   }
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
-    const int c0 = (threadIdx.x + k * FF_THREADS) * 8;
+    const int c0 = (threadIdx.x + k * NT) * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       if (c0 + e < inner) atomicAdd(g_gamma + c0 + e, gacc[k][e]);
@@ -614,9 +688,9 @@ extern "C" int alm_geglu_ln_fwd(const void* h, int64_t ldh, int gate_off, const 
   const int grid = min(M, num_sms() * 8);
   auto* hp = (const __nv_bfloat16*)h;
   auto* gp = (__nv_bfloat16*)gn;
-  if (nch <= 1) geglu_ln_fwd_kernel<1><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
-  else if (nch == 2) geglu_ln_fwd_kernel<2><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
-  else geglu_ln_fwd_kernel<4><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
+  if (nch <= 1) geglu_ln_fwd_kernel<1, 256><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
+  else if (nch == 2) geglu_ln_fwd_kernel<2, 256><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
+  else geglu_ln_fwd_kernel<4, 256><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, gp, ldg, stats, M, inner, inner_pad);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;
@@ -646,13 +720,22 @@ extern "C" int alm_geglu_ln_bwd(const void* h, int64_t ldh, int gate_off, const 
   }
   const int nch = ceil_div(inner_pad / 8, FF_THREADS);
   ALM_REQUIRE(nch <= FF_MAX_CHUNKS, ALM_ERR_UNSUPPORTED);
-  const int grid = min(M, num_sms() * 4);
   auto* hp = (const __nv_bfloat16*)h;
   auto* dg = (const __nv_bfloat16*)dgn;
   auto* dhp = (__nv_bfloat16*)dh;
-  if (nch <= 1) geglu_ln_bwd_kernel<1><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
-  else if (nch == 2) geglu_ln_bwd_kernel<2><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
-  else geglu_ln_bwd_kernel<4><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+  static const int bwd_threads = getenv("ALM_GEGLU_BWD_THREADS") ? atoi(getenv("ALM_GEGLU_BWD_THREADS")) : 512;
+  if (bwd_threads == 512 && inner_pad > 2048 && inner_pad <= 4096) {
+    // one 8-column chunk per thread: half the registers of the 256-thread layout -> 2 x 512 threads per SM
+    const int grid = min(M, num_sms() * 2);
+    geglu_ln_bwd_kernel<1, 512><<<grid, 512, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+    ALM_CHECK_LAUNCH();
+    ALM_LAUNCHED(1);
+    return ALM_OK;
+  }
+  const int grid = min(M, num_sms() * 4);
+  if (nch <= 1) geglu_ln_bwd_kernel<1, 256><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+  else if (nch == 2) geglu_ln_bwd_kernel<2, 256><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
+  else geglu_ln_bwd_kernel<4, 256><<<grid, FF_THREADS, 0, stream>>>(hp, ldh, gate_off, gamma, stats, dg, ldg, dhp, g_gamma, M, inner, inner_pad);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;

@@ -354,9 +354,18 @@ def scale_by_scalar(x, s):
 PAD_MODES = {"reflect": 0, "constant": 1, "zeros": 1, "replicate": 2}
 
 
-def causal_conv1d(x, weight, bias=None, *, stride=1, dilation=1, pad_mode="reflect", elu=False, residual=None):
-    """CausalConv1d forward (soundstream.py:332-345) with optional fused ELU and skip add. fp32 [B,C,T]."""
-    _check_cuda(x, weight, bias, residual)
+# (K, stride, dilation) shapes with a register-tiled specialisation (csrc/conv_tiled.cuh)
+CONV_TILED_SHAPES = {(7, 1, 1), (7, 1, 3), (7, 1, 9), (1, 1, 1), (3, 1, 1), (4, 2, 1), (6, 3, 1), (8, 4, 1), (10, 5, 1),
+                     (16, 8, 1)}
+
+
+def causal_conv1d(x, weight, bias=None, *, stride=1, dilation=1, pad_mode="reflect", elu=False, residual=None,
+                  weight_packed=None):
+    """CausalConv1d forward (soundstream.py:332-345) with optional fused ELU and skip add. fp32 [B,C,T].
+
+    weight [Cout, Cin, K] (torch layout); weight_packed: optional cached copy [Cin, K, Cout] (weight.permute(1, 2, 0))
+    that lets the register-tiled kernel stage weights with coalesced loads."""
+    _check_cuda(x, weight, bias, residual, weight_packed)
     assert x.dtype == f32 and weight.dtype == f32
     x = x.contiguous()
     B, Cin, T = x.shape
@@ -368,8 +377,16 @@ def causal_conv1d(x, weight, bias=None, *, stride=1, dilation=1, pad_mode="refle
     if residual is not None:
         residual = residual.contiguous()
         assert residual.shape == y.shape
-    _lib.call("alm_causal_conv1d_fwd", x, weight.contiguous(), None if bias is None else bias.contiguous(), residual,
-              y, B, Cin, Cout, T, K, stride, dilation, PAD_MODES[pad_mode], int(elu))
+    packed = weight_packed is not None and (K, stride, dilation) in CONV_TILED_SHAPES
+    if packed:
+        assert weight_packed.shape == (Cin, K, Cout) and weight_packed.is_contiguous() and weight_packed.dtype == f32
+    cls = "causal_conv1d"
+    if _PROFILE is not None and PROFILE_SHAPES:
+        cls += f" Cin{Cin} Cout{Cout} K{K} s{stride} d{dilation} T{T}"
+    with _timed(cls, 2.0 * B * Cout * Tout * Cin * K):
+        _lib.call("alm_causal_conv1d_fwd", x, weight_packed if packed else weight.contiguous(),
+                  None if bias is None else bias.contiguous(), residual, y, B, Cin, Cout, T, K, stride, dilation,
+                  PAD_MODES[pad_mode], int(elu), int(packed))
     return y
 
 
@@ -397,7 +414,8 @@ def rvq_encode(x, codebooks):
     quant = torch.empty(N, D, device=x.device, dtype=f32)
     idx = torch.empty(N, Q, device=x.device, dtype=torch.int64)
     ws = torch.empty(Q * C, device=x.device, dtype=f32)
-    _lib.call("alm_rvq_encode", x, x.stride(0), codebooks, ws, quant, D, idx, Q, N, D, C, Q)
+    with _timed("rvq_encode", 2.0 * N * Q * C * D):
+        _lib.call("alm_rvq_encode", x, x.stride(0), codebooks, ws, quant, D, idx, Q, N, D, C, Q)
     return quant, idx
 
 

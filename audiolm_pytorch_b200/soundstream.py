@@ -35,10 +35,21 @@ class CausalConv1d(nn.Module):
         self.pad_mode = pad_mode
         self.causal_padding = self.dilation * (kernel_size - 1) + (1 - self.stride)
         self.conv = nn.Conv1d(chan_in, chan_out, kernel_size, **kwargs)
+        self._packed = (None, None)  # (weight version key, [Cin, K, Cout] copy for the register-tiled kernel)
+
+    def _packed_weight(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if self._packed[0] != key:
+            with torch.no_grad():
+                self._packed = (key, w.detach().permute(1, 2, 0).contiguous())
+        return self._packed[1]
 
     def forward(self, x, elu=False, residual=None):
+        k = self.conv.kernel_size[0]
+        wp = self._packed_weight() if (k, self.stride, self.dilation) in ops.CONV_TILED_SHAPES else None
         return ops.causal_conv1d(x, self.conv.weight, self.conv.bias, stride=self.stride, dilation=self.dilation,
-                                 pad_mode=self.pad_mode, elu=elu, residual=residual)
+                                 pad_mode=self.pad_mode, elu=elu, residual=residual, weight_packed=wp)
 
 
 class CausalConvTranspose1d(nn.Module):

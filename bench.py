@@ -180,13 +180,21 @@ def codec_encode_bench(dev, clips=32, iters=5):
             ss(wave, return_encoded=True)
         b.record()
         torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / iters
+        ms = a.elapsed_time(b) / iters
+        from audiolm_pytorch_b200 import ops
+        ops.profile_start()
+        ss(wave, return_encoded=True)
+        prof = ops.profile_stop()
     frames = clips * 150
-    enc_gflop = 18.4 * clips
+    kern = {cls: {"ms_per_call": ms_, "launches": n_, "tflops_fp32": work / (ms_ * 1e-3) / 1e12 if ms_ else 0.0}
+            for cls, (ms_, work, n_) in prof.items()}
+    conv = kern.get("causal_conv1d", {})
     return {"metric": "SoundStream frames/sec encode", "value": frames / (ms * 1e-3), "unit": "frames/s",
-            "ms_per_call": ms, "clips": clips, "samples_per_clip": 48000,
-            "conv_tflops_fp32": enc_gflop / ms, "note": "fp32 CUDA-core direct convs + RVQ: FMA-bound, not HBM-bound "
-            "(133.8 MB algorithmic I/O per clip would take 21 us at the measured HBM peak)"}
+            "ms_per_call": ms, "clips": clips, "samples_per_clip": 48000, "kernels": kern,
+            # fp32 FMA peak of the part: SMs x 128 lanes x 2 FLOP x SM clock
+            "conv_frac_of_fp32_fma_peak": conv.get("tflops_fp32", 0.0) / (148 * 128 * 2 * 1.965e9 / 1e12),
+            "note": "fp32 CUDA-core convs + RVQ search (bit-exact code indices vs the fp32 oracle): FMA-bound, not "
+                    "HBM-bound (133.8 MB algorithmic I/O per clip would take 21 us at the measured HBM peak)"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -193,10 +193,13 @@ int alm_scale_by_scalar_bf16(void* x, const float* s, int64_t n, alm_stream_t st
  * act_elu = 1 applies ELU(alpha=1) before the residual add, which fuses a ResidualUnit
  * (soundstream.py:362-369) into two launches: conv_k7(dil)+ELU, then conv_k1+ELU+skip.
  * x [B,Cin,T], w [Cout,Cin,K], y [B,Cout,T/stride], all contiguous fp32.
+ * w_packed = 1: w is the pre-transposed copy [Cin,K,Cout] (coalesced weight staging of the register-tiled
+ * kernel; only for the (K, stride, dilation) shapes SoundStream uses: (7,1,{1,3,9}), (1,1,1), (3,1,1), (2s,s,1)
+ * for s in 2,3,4,5,8 - other shapes take the generic kernel and need the torch layout).
  */
 int alm_causal_conv1d_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int B,
                           int Cin, int Cout, int T, int K, int stride, int dilation, int pad_mode, int act_elu,
-                          alm_stream_t stream);
+                          int w_packed, alm_stream_t stream);
 /* CausalConvTranspose1d (soundstream.py:347-360): kernel 2*stride, output trimmed to n*stride;
  * x [B,Cin,n], w [Cin,Cout,2*stride], y [B,Cout,n*stride]; polyphase form, 2 taps per input channel. */
 int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,

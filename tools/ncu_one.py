@@ -51,9 +51,11 @@ for _ in range(3):
         gn, st = ops.geglu_ln_fwd(h, g, inner=2730, inner_pad=2736)
         ops.geglu_ln_bwd(h, g, st, rnd(M, 2736), torch.zeros_like(g), inner=2730, inner_pad=2736)
     elif which == "rvq":
-        ops.rvq_encode(rnd(9600, 512, dt=torch.float32), rnd(8, 1024, 512, dt=torch.float32))
+        ops.rvq_encode(rnd(4800, 512, dt=torch.float32), rnd(8, 1024, 512, dt=torch.float32))
     elif which == "conv":
-        x = rnd(8, 64, 24000, dt=torch.float32)
-        ops.causal_conv1d(x, rnd(64, 64, 7, dt=torch.float32, k=0.05), rnd(64, dt=torch.float32), dilation=9, elu=True)
+        x = rnd(32, 64, 24000, dt=torch.float32)
+        w = rnd(64, 64, 7, dt=torch.float32, k=0.05)
+        ops.causal_conv1d(x, w, rnd(64, dt=torch.float32), dilation=9, elu=True,
+                          weight_packed=w.permute(1, 2, 0).contiguous())
 torch.cuda.synchronize()
 print("done", which)
