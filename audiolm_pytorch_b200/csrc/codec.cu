@@ -457,10 +457,9 @@ extern "C" int alm_causal_conv1d_fwd(const float* x, const float* w, const float
   ALM_REQUIRE(pad_mode != 0 || pad < T, ALM_ERR_ARG);  // reflect needs pad < T (as F.pad does)
   const int Tout = (T + pad - dilation * (K - 1) - 1) / stride + 1;
   {
-    static const bool tiled = getenv("ALM_CONV_V1") == nullptr;  // A/B switch: first-generation kernel
-    if (tiled || w_packed) {
+    if (w_packed) {  // register-tiled kernels read the packed [Cin][K][Cout] weight copy
       const int rc = cvt::dispatch(x, w, bias, residual, y, B, Cin, Cout, T, Tout, K, stride, dilation, pad, pad_mode,
-                                   act_elu, w_packed, stream);
+                                   act_elu, stream);
       if (rc != -1) return rc;
     }
   }

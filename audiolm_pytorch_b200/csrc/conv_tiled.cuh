@@ -9,6 +9,9 @@
 //     issues COT/4 broadcast LDS.128 for the weights + TQ conflict-free LDS.32 for the samples and COT*TQ FMAs;
 //   * the staged input is split by phase (sample p -> xs[c][p % S][p / S]) so strided convs read consecutive
 //     words across a warp as well;
+//   * input-channel stages are double buffered with cp.async (zero-fill handles padding and ragged edges), so the
+//     global-load latency of stage n+1 hides behind the FMAs of stage n (the synchronous version lost 25 % of its
+//     issue slots to long-scoreboard stalls, profiles/r01_ncu_conv_tiled_k7d9.txt);
 //   * the accumulation order per output is unchanged (input channels ascending, taps ascending, one fp32 FMA
 //     chain), so results are bit-identical to the first-generation kernel and the RVQ indices stay bit-exact.
 // fp32 on CUDA cores is deliberate: the RVQ code search downstream is compared bit-exactly against the fp32
@@ -19,10 +22,13 @@
 namespace alm {
 namespace cvt {
 
-constexpr int THREADS = 256, CI = 8;
+constexpr int THREADS = 256;
+// input channels per pipeline stage: more for short kernels so a stage carries enough FMAs to hide its copies
+__host__ __device__ constexpr int ci_of(int K) { return K == 1 ? 32 : (K <= 4 ? 16 : (K <= 10 ? 8 : 4)); }
 
 template <int K, int S, int D, int TQ>
 struct Geo {
+  static constexpr int CI = ci_of(K);
   static constexpr int T_TILE = 32 * TQ;
   static constexpr int SPAN = (T_TILE - 1) * S + (K - 1) * D + 1;  // padded-signal samples per tile and channel
   static constexpr int LI = (SPAN + S - 1) / S + 1;                 // row length of one phase (+1: bank skew)
@@ -30,20 +36,32 @@ struct Geo {
 };
 
 template <int K, int S, int D, int COT, int TQ>
-constexpr size_t smem_bytes() {
-  return (size_t)(Geo<K, S, D, TQ>::XS + CI * K * 8 * COT) * sizeof(float);
+constexpr size_t smem_bytes() {  // two pipeline stages of (samples + weights)
+  return 2 * (size_t)(Geo<K, S, D, TQ>::XS + Geo<K, S, D, TQ>::CI * K * 8 * COT) * sizeof(float);
 }
 
-template <int K, int S, int D, int COT, int TQ>
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 4 : 0;  // src-size 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16f(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+// w is the PACKED weight copy [Cin][K][Cout].  VEC: Cout % 4 == 0 (16-byte weight copies).
+template <int K, int S, int D, int COT, int TQ, bool VEC>
 __global__ void __launch_bounds__(THREADS, 2)
 conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
             const float* __restrict__ residual, float* __restrict__ y, int Cin, int Cout, int T, int Tout, int pad,
-            int pad_mode, int act, int w_packed) {
+            int pad_mode, int act) {
   using G = Geo<K, S, D, TQ>;
+  constexpr int CI = G::CI;
   constexpr int CO_TILE = 8 * COT;
-  extern __shared__ float smem[];
-  float* xs = smem;            // [CI][S][LI]
-  float* ws = smem + G::XS;    // [CI][K][CO_TILE]
+  constexpr int STAGE = G::XS + CI * K * CO_TILE;  // floats per pipeline stage
+  extern __shared__ __align__(16) float smem[];
   const int t0 = blockIdx.x * G::T_TILE, o0 = blockIdx.y * CO_TILE, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int in0 = t0 * S;
@@ -53,46 +71,55 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
 #pragma unroll
     for (int q = 0; q < TQ; ++q) acc[i][q] = 0.f;
 
-  for (int c0 = 0; c0 < Cin; c0 += CI) {
-    __syncthreads();
-    {  // stage the samples: warp <-> input channel, lanes along time (coalesced), phase-split on the way in
-      const int c = warp;
+  // asynchronous copy of one stage (CI input channels of samples + their weights) into buffer `buf`
+  auto issue_stage = [&](int c0, int buf) {
+    float* xs = smem + buf * STAGE;
+    float* ws = xs + G::XS;
+    // samples: warp <-> input channel(s), lanes along time (coalesced), phase-split on the way in
+    for (int c = warp; c < CI; c += THREADS / 32) {
       const bool cok = c0 + c < Cin;
-      const float* xrow = x + ((size_t)b * Cin + c0 + c) * T;
+      const float* xrow = x + ((size_t)b * Cin + (cok ? c0 + c : 0)) * T;
       float* xrow_s = xs + c * (S * G::LI);
       for (int p = lane; p < G::SPAN; p += 32) {
-        float v = 0.f;
-        if (cok) {
-          const int i = in0 + p;
-          int src = i - pad;
-          if (i < pad) src = pad_mode == 0 ? pad - i : (pad_mode == 1 ? -1 : 0);
-          if (src >= 0 && src < T) v = __ldg(xrow + src);
-        }
-        xrow_s[(p % S) * G::LI + p / S] = v;
+        const int i = in0 + p;
+        int src = i - pad;
+        if (i < pad) src = pad_mode == 0 ? pad - i : (pad_mode == 1 ? -1 : 0);
+        const bool ok = cok && src >= 0 && src < T;
+        cp_async4(xrow_s + (p % S) * G::LI + p / S, xrow + (ok ? src : 0), ok);
       }
     }
-    // stage the weights -> ws[c][j][o]
-    if (w_packed) {
-      // pre-transposed copy [Cin][K][Cout]: consecutive threads read consecutive output channels (coalesced) and
-      // write consecutive words (conflict-free)
-      for (int i = threadIdx.x; i < CO_TILE * CI * K; i += THREADS) {
-        const int o = i % CO_TILE, r = i / CO_TILE;  // r = c * K + j
-        float v = 0.f;
-        if (o0 + o < Cout && c0 + r / K < Cin) v = __ldg(w + ((size_t)c0 * K + r) * Cout + o0 + o);
-        ws[r * CO_TILE + o] = v;
+    // weights -> ws[c][j][o] from the packed copy [Cin][K][Cout]
+    if constexpr (VEC) {
+      for (int i = threadIdx.x; i < CI * K * (CO_TILE / 4); i += THREADS) {
+        const int o4 = i % (CO_TILE / 4), r = i / (CO_TILE / 4);  // r = c * K + j
+        const bool ok = o0 + o4 * 4 < Cout && c0 + r / K < Cin;
+        cp_async16f(ws + r * CO_TILE + o4 * 4, w + (ok ? ((size_t)c0 * K + r) * Cout + o0 + o4 * 4 : 0), ok);
       }
     } else {
-      // torch layout w[o][c][j]: runs of CI*K contiguous floats per output channel (slow path: strided smem writes)
-      for (int i = threadIdx.x; i < CO_TILE * CI * K; i += THREADS) {
-        const int o = i / (CI * K), r = i - o * (CI * K);
-        float v = 0.f;
-        if (o0 + o < Cout && c0 + r / K < Cin) v = __ldg(w + ((size_t)(o0 + o) * Cin + c0) * K + r);
-        ws[r * CO_TILE + o] = v;
+      for (int i = threadIdx.x; i < CI * K * CO_TILE; i += THREADS) {
+        const int o = i % CO_TILE, r = i / CO_TILE;
+        const bool ok = o0 + o < Cout && c0 + r / K < Cin;
+        cp_async4(ws + r * CO_TILE + o, w + (ok ? ((size_t)c0 * K + r) * Cout + o0 + o : 0), ok);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int n_st = (Cin + CI - 1) / CI;
+  issue_stage(0, 0);
+  for (int st = 0; st < n_st; ++st) {
+    if (st + 1 < n_st) {
+      issue_stage((st + 1) * CI, (st + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
+    const float* xs = smem + (st & 1) * STAGE;
+    const float* ws = xs + G::XS;
+    const int c_lim = min(CI, Cin - st * CI);  // channels past Cin were zero-filled; skipping them saves time only
 #pragma unroll 1
-    for (int c = 0; c < CI; ++c) {
+    for (int c = 0; c < c_lim; ++c) {
       const float* xc = xs + c * (S * G::LI) + lane;
       const float* wc = ws + c * (K * CO_TILE) + warp * COT;
 #pragma unroll
@@ -112,6 +139,7 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
           for (int q = 0; q < TQ; ++q) acc[i][q] = fmaf(wv[i], xv[q], acc[i][q]);
       }
     }
+    __syncthreads();  // the buffer just consumed is refilled by the copy issued at the top of the next iteration
   }
 #pragma unroll
   for (int i = 0; i < COT; ++i) {
@@ -131,34 +159,36 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
   }
 }
 
-template <int K, int S, int D, int COT, int TQ>
+template <int K, int S, int D, int COT, int TQ, bool VEC>
 inline int launch(const float* x, const float* w, const float* bias, const float* residual, float* y, int B, int Cin,
-                  int Cout, int T, int Tout, int pad, int pad_mode, int act, int w_packed, cudaStream_t stream) {
+                  int Cout, int T, int Tout, int pad, int pad_mode, int act, cudaStream_t stream) {
   constexpr size_t smem = smem_bytes<K, S, D, COT, TQ>();
   static_assert(smem <= 100 * 1024, "conv tile does not fit two CTAs per SM");
   static bool attr = false;
   if (!attr) {
-    ALM_CUDA_OK(cudaFuncSetAttribute(conv_kernel<K, S, D, COT, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ALM_CUDA_OK(cudaFuncSetAttribute(conv_kernel<K, S, D, COT, TQ, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
     attr = true;
   }
   dim3 grid(ceil_div(Tout, Geo<K, S, D, TQ>::T_TILE), ceil_div(Cout, 8 * COT), B);
-  conv_kernel<K, S, D, COT, TQ><<<grid, THREADS, smem, stream>>>(x, w, bias, residual, y, Cin, Cout, T, Tout, pad,
-                                                                  pad_mode, act, w_packed);
+  conv_kernel<K, S, D, COT, TQ, VEC><<<grid, THREADS, smem, stream>>>(x, w, bias, residual, y, Cin, Cout, T, Tout, pad,
+                                                                       pad_mode, act);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;
 }
 
-// returns -1 when (K, stride, dilation) is not one of the specialised shapes
+// w must be the packed [Cin][K][Cout] copy.  Returns -1 when (K, stride, dilation) has no specialisation.
 inline int dispatch(const float* x, const float* w, const float* bias, const float* residual, float* y, int B, int Cin,
                     int Cout, int T, int Tout, int K, int stride, int dil, int pad, int pad_mode, int act,
-                    int w_packed, cudaStream_t stream) {
-#define CVT_CASE(KK, SS, DD, TQQ)                                                                                  \
-  if (K == KK && stride == SS && dil == DD) {                                                                      \
-    if (Cout >= 64)                                                                                                \
-      return launch<KK, SS, DD, 8, TQQ>(x, w, bias, residual, y, B, Cin, Cout, T, Tout, pad, pad_mode, act, w_packed, stream); \
-    return launch<KK, SS, DD, 4, TQQ>(x, w, bias, residual, y, B, Cin, Cout, T, Tout, pad, pad_mode, act, w_packed, stream);  \
+                    cudaStream_t stream) {
+  const bool vec = Cout % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15u) == 0;
+#define CVT_ARGS x, w, bias, residual, y, B, Cin, Cout, T, Tout, pad, pad_mode, act, stream
+#define CVT_CASE(KK, SS, DD, TQQ)                                             \
+  if (K == KK && stride == SS && dil == DD) {                                 \
+    if (!vec) return launch<KK, SS, DD, 4, TQQ, false>(CVT_ARGS);             \
+    if (Cout >= 64) return launch<KK, SS, DD, 8, TQQ, true>(CVT_ARGS);        \
+    return launch<KK, SS, DD, 4, TQQ, true>(CVT_ARGS);                        \
   }
   CVT_CASE(7, 1, 1, 8)
   CVT_CASE(7, 1, 3, 8)
@@ -171,6 +201,7 @@ inline int dispatch(const float* x, const float* w, const float* bias, const flo
   CVT_CASE(10, 5, 1, 4)
   CVT_CASE(16, 8, 1, 4)
 #undef CVT_CASE
+#undef CVT_ARGS
   return -1;
 }
 
