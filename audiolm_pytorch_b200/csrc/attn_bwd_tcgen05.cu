@@ -90,7 +90,9 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* s_full = qdo_empty + AB_STAGES;
   uint64_t* p_full = s_full + 1;
   uint64_t* acc_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* tmem_free = acc_full + 1;   // compute -> MMA: S^T / dP^T of this iteration are in registers
+  uint64_t* pds_free = tmem_free + 1;   // MMA -> compute: dV / dK MMAs of this iteration consumed P^T / dS^T
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pds_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // heaviest key blocks first across ALL batches (LPT order): CTA x -> (kb = x / b, batch = x % b).  With the
@@ -111,6 +113,8 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(s_full, 1);
     mbar_init(p_full, 16);
     mbar_init(acc_full, 1);
+    mbar_init(tmem_free, 16);
+    mbar_init(pds_free, 1);
     fence_mbar_init();
   }
   if (warp == AB_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -165,6 +169,17 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_after_sync();
       issue_s(0);
       for (int it = 0; it < n_iter; ++it) {
+        // software pipeline: as soon as the compute warps hold S^T / dP^T of iteration `it` in registers, the next
+        // iteration's S^T / dP^T MMAs are issued, so they run under this iteration's exp / dS arithmetic
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == AB_STAGES) { nstage = 0; nphase ^= 1u; }
+        if (it + 1 < n_iter) {
+          mbar_wait(tmem_free, it & 1);
+          mbar_wait(&qdo_full[nstage], nphase);
+          tc_fence_after_sync();
+          issue_s(nstage);
+        }
         mbar_wait(p_full, it & 1);
         tc_fence_after_sync();
         const uint32_t q_addr = smem_u32(sQ + stage * AB_TILE), do_addr = smem_u32(sdO + stage * AB_TILE);
@@ -177,13 +192,10 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           umma_bf16_ss(tmem_dK, umma_smem_desc_sw128(dst_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
                        umma_smem_desc_sw128(q_addr + k * 2048, 1024, 0), idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&qdo_empty[stage]);
+        umma_commit(pds_free);
         if (it == n_iter - 1) umma_commit(acc_full);
-        if (++stage == AB_STAGES) { stage = 0; phase ^= 1u; }
-        if (it + 1 < n_iter) {
-          mbar_wait(&qdo_full[stage], phase);
-          tc_fence_after_sync();
-          issue_s(stage);
-        }
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else {
@@ -203,7 +215,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       [[maybe_unused]] const long long bias_base =
           HAS_BIAS ? (long long)(it / q_per_head) * p.bias_hs + min(kj, p.n_k - 1) : 0;
       mbar_wait(&qdo_full[stage], phase);  // lse / delta staged in smem
-      mbar_wait(s_full, it & 1);           // S^T, dP^T ready; previous P^T/dS^T operands consumed
+      mbar_wait(s_full, it & 1);           // S^T, dP^T ready
       tc_fence_after_sync();
       const float* lse_s = sLse + stage * AB_T;
       const float* del_s = sDelta + stage * AB_T;
@@ -216,31 +228,62 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tmem_ld_32x32b_x32(tmem_ST + lane_sel + c * 32, rs);
         tmem_ld_32x32b_x32(tmem_dPT + lane_sel + c * 32, rp);
         tmem_ld_wait();
+        // S^T / dP^T are in registers: let the MMA warp overwrite them with the next iteration's products
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_free);
+        // P^T / dS^T staging tiles are still read by the previous iteration's dV / dK MMAs
+        if (it > 0) mbar_wait(pds_free, (it - 1) & 1);
+        if (!HAS_BIAS && tile_full) {
+          // fast path (88 % of the tiles at C3): no per-element predicates; a masked / out-of-range key row is
+          // zeroed through its scale factors.  lse / delta come as 16-byte shared loads.
+          const float keyf = key_ok ? 1.f : 0.f;
+          const float sc = key_ok ? p.scale : 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float pv[8], dsv[8];
+          for (int g = 0; g < 4; ++g) {
+            float pv[8], dsv[8];
+            const float4 l0 = *reinterpret_cast<const float4*>(lse_s + c * 32 + g * 8);
+            const float4 l1 = *reinterpret_cast<const float4*>(lse_s + c * 32 + g * 8 + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(del_s + c * 32 + g * 8);
+            const float4 d1 = *reinterpret_cast<const float4*>(del_s + c * 32 + g * 8 + 4);
+            const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const float dv8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = c * 32 + g * 8 + e;
-            const int qi = q0 + col;
-            const bool ok = key_ok && (tile_full || (qi < p.n_q && (!p.causal || kj <= qi + off)));
-            const float s = __uint_as_float(rs[g * 8 + e]);
-            float shift = -lse_s[col];
-            [[maybe_unused]] long long bidx = 0;
-            if constexpr (HAS_BIAS) {  // lanes hold consecutive keys of one query row: coalesced
-              bidx = bias_base + (long long)min(qi, p.n_q - 1) * p.bias_rs;
-              shift = fmaf(__ldg(p.bias + bidx), LOG2E, shift);
+            for (int e = 0; e < 8; ++e) {
+              const float pe = ex2_approx(fmaf(__uint_as_float(rs[g * 8 + e]), p.scale_log2, -lv[e]));
+              pv[e] = pe * keyf;
+              dsv[e] = (pe * sc) * (__uint_as_float(rp[g * 8 + e]) - dv8[e]);
             }
-            const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, shift)) : 0.f;
-            pv[e] = pe;
-            const float ds = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - del_s[col]) : 0.f;
-            dsv[e] = ds * p.scale;
-            if constexpr (HAS_BIAS) {
-              if (ok && p.dbias != nullptr) atomicAdd(p.dbias + bidx, ds);
-            }
+            store_a_chunk(sPT, row, c * 4 + g, pv);
+            store_a_chunk(sdST, row, c * 4 + g, dsv);
           }
-          store_a_chunk(sPT, row, c * 4 + g, pv);
-          store_a_chunk(sdST, row, c * 4 + g, dsv);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pv[8], dsv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = c * 32 + g * 8 + e;
+              const int qi = q0 + col;
+              const bool ok = key_ok && (tile_full || (qi < p.n_q && (!p.causal || kj <= qi + off)));
+              const float s = __uint_as_float(rs[g * 8 + e]);
+              float shift = -lse_s[col];
+              [[maybe_unused]] long long bidx = 0;
+              if constexpr (HAS_BIAS) {  // lanes hold consecutive keys of one query row: coalesced
+                bidx = bias_base + (long long)min(qi, p.n_q - 1) * p.bias_rs;
+                shift = fmaf(__ldg(p.bias + bidx), LOG2E, shift);
+              }
+              const float pe = ok ? ex2_approx(fmaf(s, p.scale_log2, shift)) : 0.f;
+              pv[e] = pe;
+              const float ds = ok ? pe * (__uint_as_float(rp[g * 8 + e]) - del_s[col]) : 0.f;
+              dsv[e] = ds * p.scale;
+              if constexpr (HAS_BIAS) {
+                if (ok && p.dbias != nullptr) atomicAdd(p.dbias + bidx, ds);
+              }
+            }
+            store_a_chunk(sPT, row, c * 4 + g, pv);
+            store_a_chunk(sdST, row, c * 4 + g, dsv);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -313,7 +356,9 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* s_full = kv_empty + AB_STAGES;
   uint64_t* p_full = s_full + 1;
   uint64_t* acc_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* tmem_free = acc_full + 1;  // compute -> MMA: S / dP of this tile are in registers
+  uint64_t* ds_free = tmem_free + 1;   // MMA -> compute: the dQ MMAs of this tile consumed the dS staging tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ds_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qblocks = (p.n_q + AB_T - 1) / AB_T;
@@ -332,6 +377,8 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(s_full, 1);
     mbar_init(p_full, 16);
     mbar_init(acc_full, 1);
+    mbar_init(tmem_free, 16);
+    mbar_init(ds_free, 1);
     fence_mbar_init();
   }
   if (warp == AB_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -380,6 +427,17 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_after_sync();
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
+        // software pipeline (see the dK/dV kernel): the next tile's S / dP MMAs are issued as soon as the compute
+        // warps hold this tile's S / dP in registers
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == AB_STAGES) { nstage = 0; nphase ^= 1u; }
+        if (j + 1 < n_tiles) {
+          mbar_wait(tmem_free, j & 1);
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after_sync();
+          issue_s(nstage);
+        }
         mbar_wait(p_full, j & 1);
         tc_fence_after_sync();
         const uint32_t k_addr = smem_u32(sK + stage * AB_TILE);
@@ -388,13 +446,10 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           umma_bf16_ss(tmem_dQ, umma_smem_desc_sw128(ds_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
                        umma_smem_desc_sw128(k_addr + k * 2048, 1024, 0), idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[stage]);
+        umma_commit(ds_free);
         if (j == n_tiles - 1) umma_commit(acc_full);
-        if (++stage == AB_STAGES) { stage = 0; phase ^= 1u; }
-        if (j + 1 < n_tiles) {
-          mbar_wait(&kv_full[stage], phase);
-          tc_fence_after_sync();
-          issue_s(stage);
-        }
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else {
@@ -422,6 +477,23 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, rs);
         tmem_ld_32x32b_x32(tmem_dP + lane_sel + c * 32, rp);
         tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_free);
+        if (j > 0) mbar_wait(ds_free, (j - 1) & 1);  // previous tile's dQ MMAs still read the dS staging tiles
+        if (!HAS_BIAS && tile_full) {
+          const float nlse = -lse;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float dsv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float pe = ex2_approx(fmaf(__uint_as_float(rs[g * 8 + e]), p.scale_log2, nlse));
+              dsv[e] = (pe * p.scale) * (__uint_as_float(rp[g * 8 + e]) - delta);
+            }
+            store_a_chunk(sdS, row, c * 4 + g, dsv);
+          }
+        } else
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float dsv[8];
