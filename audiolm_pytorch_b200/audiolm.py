@@ -48,6 +48,13 @@ def get_embeds(embeddings: nn.Embedding, codes, pad_id=-1, return_mask=False, ma
     return (out, ~pad) if return_mask else out
 
 
+def _tile_rows(weight, n):
+    """weight[(arange(n) % q)] as repeat + slice (audiolm_pytorch.py:903-905 does the same with einops.repeat): the
+    backward is a strided sum instead of an index_put scatter over batch x positions."""
+    q = weight.shape[0]
+    return weight.repeat(ceil_div(n, q), 1)[:n]
+
+
 def _quantizer_ids(n, q, device):
     return torch.arange(n, device=device) % q
 
@@ -115,7 +122,8 @@ class SemanticTransformer(_TokenTransformer):
         tokens = torch.cat((self.start_token.expand(ids.shape[0], 1, -1), tokens), dim=1)
         if exists(self_attn_mask):
             self_attn_mask = F.pad(self_attn_mask, (1, 0), value=True)
-        tokens, kv = self.transformer(tokens, self_attn_mask=self_attn_mask, kv_cache=kv_cache, return_kv_cache=True)
+        tokens, kv = self.transformer(tokens, self_attn_mask=self_attn_mask, kv_cache=kv_cache, return_kv_cache=True) \
+            if (return_kv_cache or exists(kv_cache)) else (self.transformer(tokens, self_attn_mask=self_attn_mask), None)
         b, n, d = tokens.shape
         logits = self._heads.linear(tokens.reshape(-1, d), self.to_logits.weight, self.to_logits.bias, "sem")
         logits = logits.view(b, n, -1)
@@ -181,7 +189,7 @@ class CoarseTransformer(_TokenTransformer):
         qid = _quantizer_ids(nc, q, dev)
         # the reference offsets ids by codebook_size (not codebook_size+1) per quantizer (:896-899)
         coarse = self.coarse_embedding(coarse_token_ids + qid * self.codebook_size)
-        coarse = coarse + self.coarse_quantize_embedding.weight[qid]
+        coarse = coarse + _tile_rows(self.coarse_quantize_embedding.weight, nc)
         sem = get_embeds(self.semantic_embedding, semantic_token_ids)
         S = sem.shape[1]
         tokens = torch.cat((self.semantic_start_token.expand(b, 1, -1), sem,
@@ -193,8 +201,10 @@ class CoarseTransformer(_TokenTransformer):
         if exists(rp):
             seq_len = tokens.shape[-2]
             attn_bias = gather_bias(rp.table(seq_len), self.cross_attn_bias, self._cross_index(seq_len, S + 1, dev))
-        tokens, new_kv = self.transformer(tokens, self_attn_mask=self_attn_mask, attn_bias=attn_bias,
-                                          kv_cache=kv_cache, return_kv_cache=True)
+        want_cache = return_cache or exists(kv_cache)
+        tokens = self.transformer(tokens, self_attn_mask=self_attn_mask, attn_bias=attn_bias, kv_cache=kv_cache,
+                                  return_kv_cache=want_cache)
+        tokens, new_kv = tokens if want_cache else (tokens, None)
         if exists(embed_cache):
             tokens = torch.cat((embed_cache.to(tokens.dtype), tokens), dim=-2)
         new_embed_cache = tokens
@@ -297,8 +307,9 @@ class FineTransformer(_TokenTransformer):
         qc, qf = self.num_coarse_quantizers, self.num_fine_quantizers
         cq, fq = _quantizer_ids(n, qc, dev), _quantizer_ids(nf, qf, dev)
         coarse = self.coarse_embedding(coarse_token_ids + cq * self.codebook_size) + \
-            self.coarse_quantize_embedding.weight[cq]
-        fine = self.fine_embedding(fine_token_ids + fq * self.codebook_size) + self.fine_quantize_embedding.weight[fq]
+            _tile_rows(self.coarse_quantize_embedding.weight, n)
+        fine = self.fine_embedding(fine_token_ids + fq * self.codebook_size) + \
+            _tile_rows(self.fine_quantize_embedding.weight, nf)
         tokens = torch.cat((self.coarse_start_token.expand(b, 1, -1), coarse,
                             self.fine_start_token.expand(b, 1, -1), fine), dim=1)
         attn_bias = None
@@ -307,8 +318,10 @@ class FineTransformer(_TokenTransformer):
             m = self.pos_bias_mlp
             table = mlp_table(mlp_in, m[0], [m[2]], m[4], self._bias_cache, "pos")
             attn_bias = gather_bias(table, self.null_pos_bias, idx)
-        tokens, new_kv = self.transformer(tokens, self_attn_mask=self_attn_mask, attn_bias=attn_bias,
-                                          kv_cache=kv_cache, return_kv_cache=True)
+        want_cache = return_cache or exists(kv_cache)
+        tokens = self.transformer(tokens, self_attn_mask=self_attn_mask, attn_bias=attn_bias, kv_cache=kv_cache,
+                                  return_kv_cache=want_cache)
+        tokens, new_kv = tokens if want_cache else (tokens, None)
         if exists(embed_cache):
             tokens = torch.cat((embed_cache.to(tokens.dtype), tokens), dim=-2)
         new_embed_cache = tokens

@@ -14,6 +14,7 @@ namespace hc2 {
 
 constexpr int S = 4, T = 5;
 constexpr int THREADS = 256;      // a CTA holds THREADS / TPT token slots; TPT = threads per token (64 or 128)
+constexpr int MAILW = 32;        // floats per warp row of the reduction mailbox (largest reduction: 28 values)
 constexpr int AUX = S * T + S + S + (S * T + S) + 2;  // ta[20] tb[4] inv[4] z[24] (pre-tanh) mean rstd
 
 template <int TPT>
@@ -23,22 +24,22 @@ __device__ __forceinline__ void bar_slot(int id) {
 
 // sum N values over the TPT threads of a token slot; all of them get the result.
 template <int N, int TPT>
-__device__ __forceinline__ void slot_sum(float (&v)[N], float* mail /*[2][TPT/32][24]*/, int& which, int w2, int lane,
+__device__ __forceinline__ void slot_sum(float (&v)[N], float* mail /*[2][TPT/32][MAILW]*/, int& which, int w2, int lane,
                                          int bar_id) {
   constexpr int WPT = TPT / 32;
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-  float* b = mail + which * (WPT * 24);
+  float* b = mail + which * (WPT * MAILW);
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) b[w2 * 24 + i] = v[i];
+    for (int i = 0; i < N; ++i) b[w2 * MAILW + i] = v[i];
   }
   bar_slot<TPT>(bar_id);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     float a = b[i];
 #pragma unroll
-    for (int w = 1; w < WPT; ++w) a += b[w * 24 + i];
+    for (int w = 1; w < WPT; ++w) a += b[w * MAILW + i];
     v[i] = a;
   }
   which ^= 1;
@@ -100,7 +101,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
                float* __restrict__ beta_out, float* __restrict__ aux, int M, int d) {
   extern __shared__ float sm[];
   constexpr int TOK = THREADS / TPT, WPT = TPT / 32;
-  float* mailbox = sm + 8 * d;  // [TOK][2][WPT][24]
+  float* mailbox = sm + 8 * d;  // [TOK][2][WPT][MAILW]
   stage_params(sm, prm, d);
   __syncthreads();
   const float* sG1 = sm;
@@ -108,7 +109,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   const float* sLn = sm + 2 * d;
   const float* sA = sm + 3 * d;
   const int slot = threadIdx.x / TPT, lt = threadIdx.x % TPT, w2 = lt >> 5, lane = lt & 31;
-  float* mail = mailbox + slot * (2 * WPT * 24);
+  float* mail = mailbox + slot * (2 * WPT * MAILW);
   int which = 0;
   const int bar_id = 1 + slot;
   const float a_scale = *prm.alpha_scale, b_scale = *prm.beta_scale;
@@ -173,23 +174,11 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
           for (int e = 0; e < 8; ++e) R[s][k][e] = 0.f;
       }
     }
-    float ssq[S];
+    // ONE reduction for the stream norms and every dynamic-map dot product: the dots are taken on the raw residual
+    // (z[s][c] = inv_s * sum_d R_s[d] g1[d] P_c[d]) so they do not have to wait for inv_s
+    float w[S * T + S + S];  // [0, S*T+S): raw dots, then S sums of squares
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < NCH; ++k)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) a = fmaf(R[s][k][e], R[s][k][e], a);
-      ssq[s] = a;
-    }
-    slot_sum<S, TPT>(ssq, mail, which, w2, lane, bar_id);
-    float inv[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) inv[s] = 1.f / fmaxf(sqrtf(ssq[s]), 1e-12f);
-    float w[S * T + S];
-#pragma unroll
-    for (int i = 0; i < S * T + S; ++i) w[i] = 0.f;
+    for (int i = 0; i < S * T + S + S; ++i) w[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       if (act[k]) {
@@ -205,7 +194,9 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
           for (int e = 0; e < 4; ++e)
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-              const float nv = R[s][k][h4 * 4 + e] * inv[s] * g1[e];
+              const float rv = R[s][k][h4 * 4 + e];
+              const float nv = rv * g1[e];
+              w[S * T + S + s] = fmaf(rv, rv, w[S * T + S + s]);
 #pragma unroll
               for (int t = 0; t < T; ++t) w[s * T + t] = fmaf(nv, av[t][e], w[s * T + t]);
               w[S * T + s] = fmaf(nv, bf[e], w[S * T + s]);
@@ -213,7 +204,15 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         }
       }
     }
-    slot_sum<S * T + S, TPT>(w, mail, which, w2, lane, bar_id);
+    slot_sum<S * T + S + S, TPT>(w, mail, which, w2, lane, bar_id);
+    float inv[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      inv[s] = 1.f / fmaxf(sqrtf(w[S * T + S + s]), 1e-12f);
+#pragma unroll
+      for (int t = 0; t < T; ++t) w[s * T + t] *= inv[s];
+      w[S * T + s] *= inv[s];
+    }
     if (lt == 0) {  // pre-activations: the backward's RMS-norm term needs them (hyper_conn_v3.cuh)
       float* az = aux + (size_t)m * AUX + S * T + S + S;
 #pragma unroll
@@ -232,7 +231,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
     }
     // mixed residual streams out; branch input kept for the LayerNorm
     float bi[NCH][8];
-    float st[1] = {0.f};
+    float st[2] = {0.f, 0.f};  // sum, sum of squares of the branch input (LayerNorm statistics in one reduction)
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
 #pragma unroll
@@ -242,6 +241,7 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         for (int s = 0; s < S; ++s) a = fmaf(alpha[s][0], R[s][k][e], a);
         bi[k][e] = a;
         st[0] += a;
+        st[1] = fmaf(a, a, st[1]);
       }
       if (act[k]) {
 #pragma unroll
@@ -259,17 +259,9 @@ pre_fwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
         *reinterpret_cast<uint4*>(bin + (size_t)m * d + ch[k]) = pack8(bi[k]);
       }
     }
-    slot_sum<1, TPT>(st, mail, which, w2, lane, bar_id);
+    slot_sum<2, TPT>(st, mail, which, w2, lane, bar_id);
     const float mean = st[0] / d;
-    float sv[1] = {0.f};
-#pragma unroll
-    for (int k = 0; k < NCH; ++k)
-      if (act[k]) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sv[0] = fmaf(bi[k][e] - mean, bi[k][e] - mean, sv[0]);
-      }
-    slot_sum<1, TPT>(sv, mail, which, w2, lane, bar_id);
-    const float rstd = rsqrtf(sv[0] / d + 1e-5f);
+    const float rstd = rsqrtf(fmaxf(st[1] / d - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
     for (int k = 0; k < NCH; ++k)
       if (act[k]) {
@@ -309,7 +301,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   extern __shared__ float sm[];
   constexpr int TOK = THREADS / TPT, WPT = TPT / 32;
   float* sGradAll = sm + 8 * d;              // [TOK][8][d]: private per token slot -> plain RMW, no atomics
-  float* mailbox = sm + (8 + 8 * TOK) * d;   // [TOK][2][WPT][24]
+  float* mailbox = sm + (8 + 8 * TOK) * d;   // [TOK][2][WPT][MAILW]
   stage_params(sm, prm, d);
   for (int i = threadIdx.x; i < 8 * TOK * d; i += blockDim.x) sGradAll[i] = 0.f;
   __syncthreads();
@@ -323,7 +315,7 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   float* gBf = sGrad + d;
   float* gLn = sGrad + 2 * d;
   float* gA = sGrad + 3 * d;
-  float* mail = mailbox + slot * (2 * WPT * 24);
+  float* mail = mailbox + slot * (2 * WPT * MAILW);
   int which = 0;
   const int bar_id = 1 + slot;
   const float sqrt_d = sqrtf((float)d);
@@ -605,9 +597,9 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
   }
 }
 
-inline size_t fwd_smem(int d, int tpt) { return (size_t)(8 * d + (THREADS / tpt) * 2 * (tpt / 32) * 24) * sizeof(float); }
+inline size_t fwd_smem(int d, int tpt) { return (size_t)(8 * d + (THREADS / tpt) * 2 * (tpt / 32) * MAILW) * sizeof(float); }
 inline size_t bwd_smem(int d, int tpt) {
-  return (size_t)((8 + 8 * (THREADS / tpt)) * d + (THREADS / tpt) * 2 * (tpt / 32) * 24) * sizeof(float);
+  return (size_t)((8 + 8 * (THREADS / tpt)) * d + (THREADS / tpt) * 2 * (tpt / 32) * MAILW) * sizeof(float);
 }
 
 }  // namespace hc2

@@ -349,6 +349,9 @@ class Transformer(nn.Module):
                 bias = bias[:, kv_cache.shape[-2]:, :]
             out, kv = self._forward_cached(x, self_attn_mask, kv_cache, bias)
         else:
+            # the [depth, 2, b, n, 64] cache tensor is only materialised when the caller asks for it (a training
+            # step does not: stacking it costs six strided copies per forward)
+            self._want_kv = bool(return_kv_cache)
             out, kv = _StackFn.apply(self, x, self_attn_mask, bias, *self._param_list())
         if not return_kv_cache:
             return out
@@ -399,7 +402,10 @@ class Transformer(nn.Module):
         last = L[-1]
         out, stats = ops.hc_post_fwd(last["R_f"], last["Y_f"], last["beta_f"], self.norm.gamma, M=M, d=d)
         # kv cache tensor [depth, 2, b, n, 64] as the reference returns it (audiolm_pytorch.py:370, 560)
-        kv_t = torch.stack([kv.view(b, n, 2, 64).permute(2, 0, 1, 3) for kv in kvs])
+        if getattr(self, "_want_kv", True):
+            kv_t = torch.stack([kv.view(b, n, 2, 64).permute(2, 0, 1, 3) for kv in kvs])
+        else:
+            kv_t = torch.empty(0, device=x.device, dtype=bf16)
         saved = dict(kv=kv_t)
         if save:
             saved.update(L=L, x2=x2, mask=mask_u8, bias=bias, stats=stats, shape=(b, n, d), x_dtype=x.dtype)
