@@ -26,8 +26,9 @@ for _ in range(3):
     if which == "gemm_ffn":
         ops.gemm(rnd(M, d), rnd(5472, d, k=0.03))
     elif which == "gemm_wgrad":
-        out = torch.zeros(5472, d, device=dev)
-        ops.gemm(rnd(M, 5472), rnd(M, d), a_mn=True, b_mn=True, out=out, acc_mode=1)
+        out = torch.zeros(2730, d, device=dev)
+        dh = rnd(M, 5472)
+        ops.gemm(dh[:, :2730], rnd(M, d), a_mn=True, b_mn=True, out=out, acc_mode=2, split_k=5)
     elif which in ("attn_fwd", "attn_bwd"):
         q, k, v = rnd(16, 2048, 512), rnd(16, 2048, 64), rnd(16, 2048, 64)
         o, lse = ops.mqa_attn_fwd(q, k, v, heads=8)
