@@ -25,6 +25,9 @@ SIGNATURES: dict[str, list] = {
     "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, L, P, L, L, I, I, I, I, I, F, P],
     "alm_mqa_attn_bwd": [P, L, P, L, L, P, L, L, P, L, P, P, P, I, P, L, P, L, P, L, P, P, L, L, I, I, I, I, I, F, P],
     "alm_attn_delta": [P, L, P, L, P, L, I, I, I, P],
+    "alm_kv_append": [P, L, P, P, L, P, I, I, P],
+    "alm_gemv_bf16": [P, L, P, L, P, I, L, P, I, I, I, P],
+    "alm_mqa_attn_decode": [P, L, P, P, L, P, I, P, L, P, L, P, I, I, I, F, P],
     "alm_bias_gather_fwd": [P, P, P, P, I, I, I, L, P],
     "alm_bias_gather_bwd": [P, P, P, P, I, I, I, L, P],
     "alm_hc_pre_fwd": [P] * 12 + [P, P, P, P, P, I, I, I, P],

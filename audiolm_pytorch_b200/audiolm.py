@@ -16,8 +16,11 @@ from torch import nn
 
 from .heads import (HeadCache, cross_entropy, generate_mask_with_prob, gumbel_sample, mask_out_after_eos_id, top_k)
 from . import ops
+from .decode import StackDecoder, TokenDecoder, engine_supported
 from .rel_pos import gather_bias, mlp_table
 from .transformer import Transformer, default, exists
+
+USE_DECODE_GRAPHS = True  # False: the decode engine runs its steps eagerly (debugging / A-B timing)
 
 __version__ = "2.4.0"  # checkpoint 'version' field of the reference this surface mirrors
 
@@ -348,6 +351,21 @@ def _eval_no_grad(fn):
     return inner
 
 
+def _cached_engine(owner, stack, batch, max_len, filter_thres, temperature, *, embed_fn, logits_fn):
+    """one TokenDecoder (static KV cache + captured graphs) per wrapper, rebuilt when shapes or weights change (the
+    graphs hold pointers to the packed bf16 weight copies of the current parameter versions)."""
+    ver = sum(p._version for p in owner.parameters())
+    max_len = -(-max_len // 256) * 256  # fewer distinct cache sizes -> fewer graph captures
+    key = (batch, max_len, float(filter_thres), float(temperature), ver, str(stack.norm.gamma.device))
+    eng = getattr(owner, "_engine", None)
+    if eng is None or eng[0] != key:
+        dec = TokenDecoder(StackDecoder(stack, batch, max_len), embed_fn, logits_fn, filter_thres=filter_thres,
+                           temperature=temperature, use_graph=USE_DECODE_GRAPHS)
+        owner._engine = eng = (key, dec)
+    eng[1].stack.set_key_mask(None)
+    return eng[1]
+
+
 def _sample_next(last_logits, filter_thres, temperature):
     """top_k(thres) + gumbel_sample (audiolm_pytorch.py:1498-1499): the uniform noise comes from torch (same
     draw as `zeros_like(t).uniform_(0, 1)`), the filter + Gumbel-max runs in one alm_topk_gumbel_sample launch."""
@@ -394,6 +412,9 @@ class SemanticTransformerWrapper(nn.Module):
             ids = batch_unique_consecutive(ids, pad_value=self.pad_id)
         batch, start = ids.shape
         out = ids.clone()
+        if (use_kv_cache and start < max_length and engine_supported(self.transformer.transformer)
+                and bool((ids != self.pad_id).all())):
+            return self._generate_graphed(out, max_length, filter_thres, temperature)
         last = (ids != self.pad_id).sum(dim=-1).long()
         kv_cache, logits = None, None
         for _ in range(start, max_length):
@@ -410,6 +431,25 @@ class SemanticTransformerWrapper(nn.Module):
             if (out == self.eos_id).any(dim=-1).all():
                 break
             last = last + 1
+        return mask_out_after_eos_id(out, self.eos_id, keep_eos=False)
+
+    def _generate_graphed(self, out, max_length, filter_thres, temperature):
+        """KV-cache sampling loop on the CUDA-graph decode engine (decode.py): the prompt goes through the normal
+        forward once, every further token is one graph replay + an EOS poll."""
+        tr = self.transformer
+        batch = out.shape[0]
+        logits, kv = tr.forward_with_cond_scale(ids=out, return_kv_cache=True)
+        out = torch.cat((out, _sample_next(logits[:, -1], filter_thres, temperature)), dim=-1)
+        dec = _cached_engine(self, tr.transformer, batch, max_length + 2, filter_thres, temperature,
+                             embed_fn=lambda tok, _key: tr.semantic_embedding(tok),
+                             logits_fn=lambda o, _key: tr._heads.linear_decode(o, tr.to_logits.weight, tr.to_logits.bias, "sem"))
+        dec.stack.load_cache(kv[0])
+        dec.tok.copy_(out[:, -1])
+        for _ in range(out.shape[1], max_length):
+            if (out == self.eos_id).any(dim=-1).all():
+                break
+            dec.advance()
+            out = torch.cat((out, dec.tok[:, None]), dim=-1)
         return mask_out_after_eos_id(out, self.eos_id, keep_eos=False)
 
     def forward(self, *, semantic_token_ids=None, raw_wave=None, text=None, text_embeds=None, return_loss=False,
@@ -448,6 +488,44 @@ def _frame_sampler(step_fn, n_quantizers, time_steps, seq, filter_thres, tempera
                 last[:, -1] = float("-inf")
             seq = torch.cat((seq, _sample_next(last, filter_thres, temperature)), dim=-1)
     return seq
+
+
+def _frame_sampler_graphed(owner, stack, step_fn, n_quantizers, time_steps, seq, filter_thres, temperature, *,
+                           embed_fn, head_fn, prefix_len, key_mask=None):
+    """`_frame_sampler` with the KV cache on the CUDA-graph decode engine (decode.py): the first token goes through
+    the normal forward (which also fills the cache), every further token is one graph replay.  One graph per
+    quantizer index of the token being fed back (embedding offset, next head, EOS rule all depend on it only).
+
+    embed_fn(tok, q) -> [b, d];  head_fn(out, q_next) -> fp32 logits of the token with quantizer index q_next."""
+    time_steps = list(time_steps)
+    total = len(time_steps) * n_quantizers
+    if total == 0:
+        return seq
+    batch = seq.shape[0]
+    logits, (kv, _) = step_fn(seq, None, None)
+    last = logits[:, -1].clone()
+    if not time_steps[0] > 0:
+        last[:, -1] = float("-inf")
+    buf = torch.empty(batch, total, device=seq.device, dtype=torch.long)
+    buf[:, 0] = _sample_next(last, filter_thres, temperature)[:, 0]
+
+    def logits_fn(out, q_in):  # EOS (the last class) only at a frame boundary (:1699-1700, 1987-1988)
+        q_next = (q_in + 1) % n_quantizers
+        lg = head_fn(out, q_next)
+        if q_next != 0:
+            lg[:, -1] = float("-inf")
+        return lg
+
+    dec = _cached_engine(owner, stack, batch, prefix_len + total + 1, filter_thres, temperature, embed_fn=embed_fn,
+                         logits_fn=logits_fn)
+    dec.stack.load_cache(kv[0])
+    if exists(key_mask):
+        dec.stack.set_key_mask(key_mask)
+    dec.tok.copy_(buf[:, 0])
+    for i in range(1, total):
+        dec.advance(key=(i - 1) % n_quantizers)
+        buf[:, i] = dec.tok
+    return torch.cat((seq, buf), dim=-1)
 
 
 class CoarseTransformerWrapper(nn.Module):
@@ -505,8 +583,19 @@ class CoarseTransformerWrapper(nn.Module):
                 return_kv_cache=True, kv_cache=kv, embed_cache=emb, return_only_coarse_logits=True, **kwargs)
             return cl, caches
 
-        seq = _frame_sampler(step, self.num_coarse_quantizers, range(0, max_time_steps), coarse.clone(),
-                             filter_thres, temperature, use_kv_cache)
+        tr = self.transformer
+        q_n = self.num_coarse_quantizers
+        if (use_kv_cache and not kwargs and engine_supported(tr.transformer) and coarse.shape[-1] % q_n == 0
+                and max_time_steps > 0):
+            cb = tr.codebook_size
+            seq = _frame_sampler_graphed(
+                self, tr.transformer, step, q_n, range(0, max_time_steps), coarse.clone(), filter_thres, temperature,
+                embed_fn=lambda tok, q: tr.coarse_embedding(tok + q * cb) + tr.coarse_quantize_embedding.weight[q],
+                head_fn=lambda o, q: tr._heads.linear_decode(o, tr.coarse_logit_weights[q], None, ("coarse", q)),
+                prefix_len=semantic_token_ids.reshape(batch, -1).shape[-1] + 2 + coarse.shape[-1])
+        else:
+            seq = _frame_sampler(step, q_n, range(0, max_time_steps), coarse.clone(), filter_thres, temperature,
+                                 use_kv_cache)
         seq = mask_out_after_eos_id(seq, self.coarse_eos_id, keep_eos=False)
         seq = seq.reshape(batch, -1, self.num_coarse_quantizers)
         if not reconstruct_wave:
@@ -621,8 +710,21 @@ class FineTransformerWrapper(nn.Module):
                 kv_cache=kv, embed_cache=emb, return_kv_cache=True, **kwargs)
             return fl, caches
 
-        seq = _frame_sampler(step, self.num_fine_quantizers, range(first, steps), fine.clone(), filter_thres,
-                             temperature, use_kv_cache)
+        tr = self.transformer
+        q_n = self.num_fine_quantizers
+        if (use_kv_cache and not kwargs and engine_supported(tr.transformer) and not exists(tr.pos_bias_mlp)
+                and fine.shape[-1] % q_n == 0 and steps > first):
+            cb = tr.codebook_size
+            # padded / eos coarse positions are never attended to (FineTransformer.forward, :1175-1184)
+            keep = F.pad((coarse != tr.pad_id) & (coarse != tr.eos_id), (1, 0), value=True)
+            seq = _frame_sampler_graphed(
+                self, tr.transformer, step, q_n, range(first, steps), fine.clone(), filter_thres, temperature,
+                embed_fn=lambda tok, q: tr.fine_embedding(tok + q * cb) + tr.fine_quantize_embedding.weight[q],
+                head_fn=lambda o, q: tr._heads.linear_decode(o, tr.fine_logit_weights[q], None, ("fine", q)),
+                prefix_len=coarse.shape[-1] + 2 + fine.shape[-1], key_mask=None if bool(keep.all()) else keep)
+        else:
+            seq = _frame_sampler(step, q_n, range(first, steps), fine.clone(), filter_thres, temperature,
+                                 use_kv_cache)
         seq = mask_out_after_eos_id(seq, self.eos_id, keep_eos=False)
         seq = seq.reshape(batch, -1, self.num_fine_quantizers)
         coarse3 = coarse.reshape(batch, -1, self.num_coarse_quantizers)

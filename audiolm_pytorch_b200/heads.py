@@ -36,6 +36,16 @@ class HeadCache:
         # forward uses the first V rows; backward (dgrad) uses all pad8(V) rows against the padded dlogits
         return _LinearPacked.apply(x2d, weight, bias, packed, V)
 
+    @torch.no_grad()
+    def linear_decode(self, x2d, weight, bias, key):
+        """inference-only logits for a handful of rows (decode step): weight-read-bound GEMV, no autograd."""
+        packed = self._pk.get(key, [weight], lambda: pack_head(weight))
+        V = weight.shape[0]
+        x = x2d.to(bf16).contiguous()
+        if x.shape[0] <= 8:
+            return ops.gemv(x, packed[:V], out_dtype=f32, bias=None if bias is None else bias.detach())
+        return ops.gemm(x, packed[:V], out_dtype=f32, bias=None if bias is None else bias.detach().float().contiguous())
+
     def grouped(self, tokens, weights, key):
         """position p of tokens [b, n, d] uses weights[p mod Q]  ->  logits [b, n, V] fp32."""
         b, n, d = tokens.shape

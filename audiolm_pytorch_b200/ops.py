@@ -190,6 +190,47 @@ def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, sca
     return dq, dk, dv
 
 
+def gemv(x, w, *, out_dtype=bf16, bias=None):
+    """x [rows <= 8, K] bf16, w [N, >=K (zero padded to a multiple of 8)] bf16 -> [rows, N] (decode-step Linear)."""
+    _check_cuda(x, w, bias)
+    rows, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == bf16 and w.dtype == bf16 and x.stride(1) == 1 and w.stride(1) == 1 and rows <= 8
+    assert w.shape[1] >= K and w.shape[1] % 8 == 0
+    out = torch.empty(rows, N, device=x.device, dtype=out_dtype)
+    _lib.call("alm_gemv_bf16", x, x.stride(0), w, w.stride(0), out, int(out_dtype == f32), out.stride(0),
+              None if bias is None else bias.float().contiguous(), rows, N, K)
+    return out
+
+
+def kv_append(kv_new, k_cache, v_cache, cache_len):
+    """k_cache[b, len] = kv_new[b, :64]; v_cache[b, len] = kv_new[b, 64:]  (len: int32 device scalar)."""
+    _check_cuda(kv_new, k_cache, v_cache, cache_len)
+    b, max_len, dh = k_cache.shape
+    assert dh == 64 and v_cache.shape == k_cache.shape and kv_new.shape == (b, 128) and kv_new.dtype == bf16
+    assert k_cache.dtype == bf16 and v_cache.dtype == bf16 and cache_len.dtype == torch.int32
+    assert k_cache.stride(1) == 64 and v_cache.stride() == k_cache.stride() and kv_new.stride(1) == 1
+    _lib.call("alm_kv_append", kv_new, kv_new.stride(0), k_cache, v_cache, k_cache.stride(0), cache_len, max_len, b)
+
+
+def mqa_attn_decode(q, k_cache, v_cache, cache_len, *, heads, key_mask=None, scale=None, splits=None):
+    """one new query per sequence against the static cache: q [b, heads*64] bf16 -> o [b, heads*64] bf16.
+    Attends keys 0..cache_len (inclusive: the new token has just been appended at position cache_len)."""
+    _check_cuda(q, k_cache, v_cache, cache_len, key_mask)
+    b, max_len, _ = k_cache.shape
+    assert q.shape == (b, heads * 64) and q.dtype == bf16 and q.stride(1) == 1
+    o = torch.empty(b, heads * 64, device=q.device, dtype=bf16)
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.shape[0] == b and key_mask.shape[1] >= max_len
+    if splits is None:  # enough CTAs to spread a long cache over the SMs, fixed per cache size (static launch)
+        splits = max(1, min(32, max_len // 128, 148 // max(1, b)))
+    ws = torch.empty(b, splits, heads, 66, device=q.device, dtype=f32) if splits > 1 else None
+    _lib.call("alm_mqa_attn_decode", q, q.stride(0), k_cache, v_cache, k_cache.stride(0), cache_len, max_len, key_mask,
+              0 if key_mask is None else key_mask.stride(0), o, o.stride(0), ws, splits, b, heads,
+              float(64 ** -0.5 if scale is None else scale))
+    return o
+
+
 def bias_gather_fwd(table, idx, override, *, ld=None):
     """table [P, H] fp32, idx [n_q, n_k] int32 (-1 = override), override [H] fp32 or None -> bias [H, n_q, ld] fp32."""
     _check_cuda(table, idx, override)

@@ -103,6 +103,27 @@ int alm_bias_gather_fwd(const float* table, const int32_t* idx, const float* ove
 int alm_bias_gather_bwd(const float* dbias, const int32_t* idx, float* dtable, float* doverride, int heads, int n_q,
                         int n_k, int64_t ld, alm_stream_t stream);
 
+/*
+ * Incremental decoding against a static KV cache (config C5).  The cache fill level is read from device memory
+ * (`len`), so a whole decode step has constant launch parameters and can be replayed from one CUDA graph:
+ *   alm_kv_append       k_cache[b, *len, :] = kv_new[b, 0:64];  v_cache[b, *len, :] = kv_new[b, 64:128]
+ *   alm_mqa_attn_decode o[b, h*64:(h+1)*64] = softmax over keys j <= *len of (q[b,h,:]·k_cache[b,j,:]*scale) · v_cache
+ * k_cache / v_cache: bf16 [b, max_len, 64] with batch stride cache_bstride (elements); key_mask (uint8 [b, >=max_len],
+ * row stride mask_bstride, 1 = attend) optional.  splits > 1 slices the keys over that many CTAs per sequence
+ * (flash-decoding) and merges the partial softmax states in a second launch.  Replaces the per-step torch.cat of the cache and the n_q = 1
+ * attention of Attention.forward (audiolm_pytorch.py:363-365, 390) inside generate (:1406-1511, 1608-1740, 1896-2039).
+ */
+/* out[r, n] = sum_k x[r, k] W[n, k] (+ bias[n]) for rows <= 8 (a decode step's Linear layers: weight-read bound;
+ * one warp per output column over all SMs).  W bf16 [N, ldw] with zero padding to a multiple of 8 columns. */
+int alm_gemv_bf16(const void* x, int64_t ldx, const void* W, int64_t ldw, void* out, int c_fp32, int64_t ldo,
+                  const float* bias, int rows, int N, int K, alm_stream_t stream);
+int alm_kv_append(const void* kv_new, int64_t ld, void* k_cache, void* v_cache, int64_t cache_bstride,
+                  const int32_t* len, int max_len, int b, alm_stream_t stream);
+int alm_mqa_attn_decode(const void* q, int64_t ldq, const void* k_cache, const void* v_cache, int64_t cache_bstride,
+                        const int32_t* len, int max_len, const void* key_mask, int64_t mask_bstride, void* o,
+                        int64_t ldo, float* workspace /* [b, splits, h, 66] fp32 when splits > 1 */, int splits, int b,
+                        int h, float scale, alm_stream_t stream);
+
 /* ---- Hyper-Connections residual streams fused with the pre-LayerNorm (HBM-bound) ---------------- */
 /*
  * Internal layout: residual streams R [M, S=4, d] bf16, M = batch*seq.  One call per branch does

@@ -45,7 +45,10 @@ def timed(name, fn, n_tokens):
     return r
 
 
-timed("semantic", lambda: sem.generate(max_length=steps, batch_size=1), steps)
+r = timed("semantic", lambda: sem.generate(max_length=steps, batch_size=1), steps)
+if r.shape[1] < steps:  # early EOS with random weights: report per generated token
+    out["semantic"]["ms_per_token"] *= steps / max(r.shape[1], 1)
+    out["semantic"]["tokens"] = int(r.shape[1])
 sem_ids = torch.randint(0, 500, (1, 500), device=dev)
 c = timed("coarse", lambda: coarse.generate(semantic_token_ids=sem_ids, max_time_steps=steps // 3), steps // 3 * 3)
 c = c.clamp(min=0)
