@@ -253,9 +253,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (p.c_fp32) {
           float* dst = reinterpret_cast<float*>(p.C) + row_off + nbase;
           if (p.acc_mode == 2) {
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+              // 16-byte vector reductions: a quarter of the L2 atomic operations of scalar red.add (the split-K
+              // weight gradients were bound by them: profiles/r01_ncu_gemm_wgrad_w1.txt, 447 MB of red traffic)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < p.N) atomicAdd(dst + j, v[j]);
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < p.N) atomicAdd(dst + j, v[j]);
+            }
           } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
