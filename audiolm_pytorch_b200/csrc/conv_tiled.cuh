@@ -65,11 +65,14 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
   const int t0 = blockIdx.x * G::T_TILE, o0 = blockIdx.y * CO_TILE, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int in0 = t0 * S;
-  float acc[COT][TQ];
+  // accumulators as float2 pairs along time: the FMAs are issued as packed fma.rn.f32x2 (FFMA2), two IEEE fp32
+  // FMAs per instruction - the kernel is issue-bound (85 % issue-active at 64 % FMA-pipe utilisation with scalar
+  // FFMA, profiles/r01_ncu_conv_tiled_cpasync.txt), and each output still sees the same single FMA chain
+  float2 acc[COT][TQ / 2];
 #pragma unroll
   for (int i = 0; i < COT; ++i)
 #pragma unroll
-    for (int q = 0; q < TQ; ++q) acc[i][q] = 0.f;
+    for (int q = 0; q < TQ / 2; ++q) acc[i][q] = make_float2(0.f, 0.f);
 
   // asynchronous copy of one stage (CI input channels of samples + their weights) into buffer `buf`
   auto issue_stage = [&](int c0, int buf) {
@@ -124,7 +127,8 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
       const float* wc = ws + c * (K * CO_TILE) + warp * COT;
 #pragma unroll
       for (int j = 0; j < K; ++j) {
-        float wv[COT], xv[TQ];
+        float wv[COT];
+        float2 xv[TQ / 2];
 #pragma unroll
         for (int i4 = 0; i4 < COT / 4; ++i4) {
           const float4 t4 = *reinterpret_cast<const float4*>(wc + j * CO_TILE + i4 * 4);
@@ -132,11 +136,13 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
         }
         const int off = ((j * D) % S) * G::LI + (j * D) / S;  // compile-time after unrolling
 #pragma unroll
-        for (int q = 0; q < TQ; ++q) xv[q] = xc[off + 32 * q];
+        for (int q = 0; q < TQ / 2; ++q) xv[q] = make_float2(xc[off + 32 * (2 * q)], xc[off + 32 * (2 * q + 1)]);
 #pragma unroll
-        for (int i = 0; i < COT; ++i)
+        for (int i = 0; i < COT; ++i) {
+          const float2 w2 = make_float2(wv[i], wv[i]);
 #pragma unroll
-          for (int q = 0; q < TQ; ++q) acc[i][q] = fmaf(wv[i], xv[q], acc[i][q]);
+          for (int q = 0; q < TQ / 2; ++q) acc[i][q] = __ffma2_rn(w2, xv[q], acc[i][q]);
+        }
       }
     }
     __syncthreads();  // the buffer just consumed is refilled by the copy issued at the top of the next iteration
@@ -150,7 +156,7 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
     for (int q = 0; q < TQ; ++q) {
       const int t = t0 + lane + 32 * q;
       if (t >= Tout) continue;
-      float v = acc[i][q] + bv;
+      float v = ((q & 1) ? acc[i][q >> 1].y : acc[i][q >> 1].x) + bv;
       if (act) v = v > 0.f ? v : expm1f(v);
       const size_t idx = ((size_t)b * Cout + o) * Tout + t;
       if (residual) v += residual[idx];
