@@ -44,6 +44,7 @@ SIGNATURES: dict[str, list] = {
     "alm_topk_gumbel_sample": [P, L, P, L, P, I, I, I, F, P],
     "alm_resid_ln_fwd": [P, P, P, P, P, P, P, I, I, P],
     "alm_resid_ln_bwd": [P, P, P, P, P, P, P, P, P, F, I, I, P],
+    "alm_residual_unit_fwd": [P, P, P, P, P, P, I, I, I, I, I, P],
     "alm_causal_conv1d_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "alm_causal_convT1d_fwd": [P, P, P, P, I, I, I, I, I, P],
     "alm_rvq_encode": [P, L, P, P, P, L, P, L, I, I, I, I, P],

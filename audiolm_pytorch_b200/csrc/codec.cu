@@ -480,6 +480,19 @@ extern "C" int alm_causal_conv1d_fwd(const float* x, const float* w, const float
   return ALM_OK;
 }
 
+extern "C" int alm_residual_unit_fwd(const float* x, const float* w7_packed, const float* b7, const float* w1_packed,
+                                     const float* b1, float* y, int B, int C, int T, int dilation, int pad_mode,
+                                     alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(x && w7_packed && b7 && w1_packed && b1 && y && B > 0 && C > 0 && T > 0 && B <= 65535, ALM_ERR_ARG);
+  ALM_REQUIRE(pad_mode >= 0 && pad_mode <= 2, ALM_ERR_ARG);
+  ALM_REQUIRE(pad_mode != 0 || 6 * dilation < T, ALM_ERR_ARG);
+  ALM_REQUIRE((reinterpret_cast<uintptr_t>(w7_packed) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w1_packed) & 15u) == 0,
+              ALM_ERR_ALIGN);
+  const int rc = cvt::dispatch_ru(x, w7_packed, b7, w1_packed, b1, y, B, C, T, dilation, pad_mode, stream);
+  return rc == -1 ? ALM_ERR_UNSUPPORTED : rc;
+}
+
 extern "C" int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin,
                                       int Cout, int n, int stride, alm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -165,6 +165,214 @@ conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused ResidualUnit (soundstream.py:362-369):  y = x + ELU(b1 + W1 . ELU(b7 + conv7_dil(x)))
+// One CTA owns ALL C channels of a time tile, so the k=7 result never leaves the SM: it is written (after bias +
+// ELU) to a [C][T_TILE] shared-memory tile and immediately contracted with the 1x1 weights.  Saves the HBM round
+// trip of the intermediate and the standalone 1x1 launch (which ran at 8-19 TFLOP/s: too little work per byte to
+// hide its own latency).  Both contractions keep the channel-ascending single-FMA-chain order of the unfused
+// kernels, so the result is bit-identical to conv7 -> conv1.
+// Thread tile: COT = C/8 channels x TQ = 64/COT samples (64 accumulators); T_TILE = 32*TQ; C * T_TILE = 16384.
+// ------------------------------------------------------------------------------------------------
+template <int C, int D>
+struct RuGeo {
+  static constexpr int K = 7;
+  static constexpr int COT = C / 8;
+  static constexpr int TQ = 64 / COT;
+  static constexpr int T_TILE = 32 * TQ;
+  static constexpr int CI = C >= 256 ? 2 : 4;  // small stages: two CTAs (16 warps) per SM with the 64 KB tile
+  static constexpr int SPAN = T_TILE - 1 + (K - 1) * D + 1;
+  static constexpr int LI = SPAN + 1;
+  static constexpr int XS = (CI * LI + 3) & ~3;      // staged samples of one stage (weights after it stay 16-B aligned)
+  static constexpr int STAGE = XS + CI * K * C;      // + its k=7 weights
+  static constexpr int CI2 = ((STAGE / C) & ~3) < 32 ? ((STAGE / C) & ~3) : 32;  // 1x1 weight rows per stage
+  static constexpr int MID = C * T_TILE;
+  static constexpr size_t SMEM = (size_t)(2 * STAGE + MID) * sizeof(float);
+};
+
+template <int C, int D>
+__global__ void __launch_bounds__(THREADS, RuGeo<C, D>::SMEM <= 113 * 1024 ? 2 : 1)
+residual_unit_kernel(const float* __restrict__ x, const float* __restrict__ w7 /*[C][7][C] packed*/,
+                     const float* __restrict__ b7, const float* __restrict__ w1 /*[C][1][C] packed*/,
+                     const float* __restrict__ b1, float* __restrict__ y, int T, int pad_mode) {
+  using G = RuGeo<C, D>;
+  constexpr int K = G::K, COT = G::COT, TQ = G::TQ, CI = G::CI, STAGE = G::STAGE;
+  extern __shared__ __align__(16) float smem[];
+  float* mid = smem + 2 * STAGE;  // [C][T_TILE]
+  const int t0 = blockIdx.x * G::T_TILE, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int pad = D * (K - 1);
+  float2 acc[COT][TQ / 2];
+#pragma unroll
+  for (int i = 0; i < COT; ++i)
+#pragma unroll
+    for (int q = 0; q < TQ / 2; ++q) acc[i][q] = make_float2(0.f, 0.f);
+
+  auto issue7 = [&](int c0, int buf) {
+    float* xs = smem + buf * STAGE;
+    float* ws = xs + G::XS;
+    for (int c = warp; c < CI; c += THREADS / 32) {
+      const float* xrow = x + ((size_t)b * C + c0 + c) * T;
+      float* xrow_s = xs + c * G::LI;
+      for (int p = lane; p < G::SPAN; p += 32) {
+        const int i = t0 + p;
+        int src = i - pad;
+        if (i < pad) src = pad_mode == 0 ? pad - i : (pad_mode == 1 ? -1 : 0);
+        const bool ok = src >= 0 && src < T;
+        cp_async4(xrow_s + p, xrow + (ok ? src : 0), ok);
+      }
+    }
+    for (int i = threadIdx.x; i < CI * K * (C / 4); i += THREADS) {
+      const int o4 = i % (C / 4), r = i / (C / 4);
+      cp_async16f(ws + r * C + o4 * 4, w7 + ((size_t)c0 * K + r) * C + o4 * 4, true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ---------------- phase A: dilated k=7 conv over all C input channels ----------------
+  constexpr int n_st = C / CI;
+  issue7(0, 0);
+  for (int st = 0; st < n_st; ++st) {
+    if (st + 1 < n_st) {
+      issue7((st + 1) * CI, (st + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* xs = smem + (st & 1) * STAGE;
+    const float* ws = xs + G::XS;
+#pragma unroll 1
+    for (int c = 0; c < CI; ++c) {
+      const float* xc = xs + c * G::LI + lane;
+      const float* wc = ws + c * (K * C) + warp * COT;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float2 xv[TQ / 2];
+#pragma unroll
+        for (int q = 0; q < TQ / 2; ++q) xv[q] = make_float2(xc[j * D + 32 * (2 * q)], xc[j * D + 32 * (2 * q + 1)]);
+#pragma unroll
+        for (int i4 = 0; i4 < COT / 4; ++i4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(wc + j * C + i4 * 4);
+          const float wv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 w2 = make_float2(wv[u], wv[u]);
+#pragma unroll
+            for (int q = 0; q < TQ / 2; ++q) acc[i4 * 4 + u][q] = __ffma2_rn(w2, xv[q], acc[i4 * 4 + u][q]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---------------- phase B: bias + ELU -> shared-memory tile; start streaming the 1x1 weights ----------------
+  auto issue1 = [&](int c0, int buf) {  // rows c0 .. c0+CI2 of the packed [C][C] matrix (row = input channel)
+    float* ws = smem + buf * STAGE;
+    for (int i = threadIdx.x; i < G::CI2 * (C / 4); i += THREADS) {
+      const int o4 = i % (C / 4), r = i / (C / 4);
+      const bool ok = c0 + r < C;
+      cp_async16f(ws + r * C + o4 * 4, w1 + (size_t)(ok ? c0 + r : 0) * C + o4 * 4, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue1(0, 0);
+#pragma unroll
+  for (int i = 0; i < COT; ++i) {
+    const int o = warp * COT + i;
+    const float bv = __ldg(b7 + o);
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) {
+      float v = ((q & 1) ? acc[i][q >> 1].y : acc[i][q >> 1].x) + bv;
+      v = v > 0.f ? v : expm1f(v);
+      mid[o * G::T_TILE + lane + 32 * q] = v;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < COT; ++i)
+#pragma unroll
+    for (int q = 0; q < TQ / 2; ++q) acc[i][q] = make_float2(0.f, 0.f);
+  // ---------------- phase C: 1x1 conv over the tile ----------------
+  constexpr int n_st1 = (C + G::CI2 - 1) / G::CI2;
+  for (int st = 0; st < n_st1; ++st) {
+    if (st + 1 < n_st1) {
+      issue1((st + 1) * G::CI2, (st + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // (first iteration: also publishes the mid tile)
+    const float* ws = smem + (st & 1) * STAGE;
+    const int c_lim = min(G::CI2, C - st * G::CI2);
+#pragma unroll 2
+    for (int c = 0; c < c_lim; ++c) {
+      const float* mc = mid + (st * G::CI2 + c) * G::T_TILE + lane;
+      const float* wc = ws + c * C + warp * COT;
+      float2 xv[TQ / 2];
+#pragma unroll
+      for (int q = 0; q < TQ / 2; ++q) xv[q] = make_float2(mc[32 * (2 * q)], mc[32 * (2 * q + 1)]);
+#pragma unroll
+      for (int i4 = 0; i4 < COT / 4; ++i4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wc + i4 * 4);
+        const float wv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 w2 = make_float2(wv[u], wv[u]);
+#pragma unroll
+          for (int q = 0; q < TQ / 2; ++q) acc[i4 * 4 + u][q] = __ffma2_rn(w2, xv[q], acc[i4 * 4 + u][q]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---------------- phase D: bias + ELU + skip ----------------
+#pragma unroll
+  for (int i = 0; i < COT; ++i) {
+    const int o = warp * COT + i;
+    const float bv = __ldg(b1 + o);
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) {
+      const int t = t0 + lane + 32 * q;
+      if (t >= T) continue;
+      float v = ((q & 1) ? acc[i][q >> 1].y : acc[i][q >> 1].x) + bv;
+      v = v > 0.f ? v : expm1f(v);
+      const size_t idx = ((size_t)b * C + o) * T + t;
+      y[idx] = v + __ldg(x + idx);
+    }
+  }
+}
+
+template <int C, int D>
+inline int launch_ru(const float* x, const float* w7, const float* b7, const float* w1, const float* b1, float* y,
+                     int B, int T, int pad_mode, cudaStream_t stream) {
+  using G = RuGeo<C, D>;
+  static_assert(G::SMEM <= 200 * 1024, "residual unit tile does not fit shared memory");
+  static bool attr = false;
+  if (!attr) {
+    ALM_CUDA_OK(cudaFuncSetAttribute(residual_unit_kernel<C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)G::SMEM));
+    attr = true;
+  }
+  dim3 grid(ceil_div(T, G::T_TILE), B);
+  residual_unit_kernel<C, D><<<grid, THREADS, G::SMEM, stream>>>(x, w7, b7, w1, b1, y, T, pad_mode);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+// -1: no specialisation for (C, dilation)
+inline int dispatch_ru(const float* x, const float* w7, const float* b7, const float* w1, const float* b1, float* y,
+                       int B, int C, int T, int dil, int pad_mode, cudaStream_t stream) {
+#define RU_CASE(CC, DD) \
+  if (C == CC && dil == DD) return launch_ru<CC, DD>(x, w7, b7, w1, b1, y, B, T, pad_mode, stream);
+  RU_CASE(32, 1) RU_CASE(32, 3) RU_CASE(32, 9)
+  RU_CASE(64, 1) RU_CASE(64, 3) RU_CASE(64, 9)
+  RU_CASE(128, 1) RU_CASE(128, 3) RU_CASE(128, 9)
+  RU_CASE(256, 1) RU_CASE(256, 3) RU_CASE(256, 9)
+#undef RU_CASE
+  return -1;
+}
+
 template <int K, int S, int D, int COT, int TQ, bool VEC>
 inline int launch(const float* x, const float* w, const float* bias, const float* residual, float* y, int B, int Cin,
                   int Cout, int T, int Tout, int pad, int pad_mode, int act, cudaStream_t stream) {

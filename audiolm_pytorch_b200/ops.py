@@ -431,6 +431,23 @@ def causal_conv1d(x, weight, bias=None, *, stride=1, dilation=1, pad_mode="refle
     return y
 
 
+RU_FUSED_CHANNELS = {32, 64, 128, 256}
+RU_FUSED_DILATIONS = {1, 3, 9}
+
+
+def residual_unit(x, w7_packed, b7, w1_packed, b1, *, dilation, pad_mode="reflect"):
+    """fused ResidualUnit forward (soundstream.py:362-369); packed weights [C,7,C] / [C,1,C], fp32 [B,C,T]."""
+    _check_cuda(x, w7_packed, b7, w1_packed, b1)
+    x = x.contiguous()
+    B, C, T = x.shape
+    assert w7_packed.shape == (C, 7, C) and w1_packed.shape == (C, 1, C) and x.dtype == f32
+    y = torch.empty_like(x)
+    with _timed("residual_unit_fused", 2.0 * B * C * T * C * 8):
+        _lib.call("alm_residual_unit_fwd", x, w7_packed, b7.contiguous(), w1_packed, b1.contiguous(), y, B, C, T,
+                  dilation, PAD_MODES[pad_mode])
+    return y
+
+
 def causal_conv_transpose1d(x, weight, bias=None, *, stride):
     """CausalConvTranspose1d forward (soundstream.py:347-360): weight [Cin, Cout, 2*stride]."""
     _check_cuda(x, weight, bias)

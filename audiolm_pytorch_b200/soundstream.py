@@ -21,6 +21,9 @@ from . import ops
 f32 = torch.float32
 
 
+FUSE_RESIDUAL_UNITS = True  # False: conv7 + conv1 as two launches (A/B tests)
+
+
 def exists(v):
     return v is not None
 
@@ -84,8 +87,15 @@ class ResidualUnit(nn.Module):
         self.fn = _RUBody(chan_in, chan_out, dilation, kernel_size, pad_mode)
 
     def forward(self, x):
-        h = getattr(self.fn, "0")(x, elu=True)
-        return getattr(self.fn, "2")(h, elu=True, residual=x)
+        c7, c1 = getattr(self.fn, "0"), getattr(self.fn, "2")
+        C = x.shape[1]
+        if (FUSE_RESIDUAL_UNITS and C in ops.RU_FUSED_CHANNELS and c7.dilation in ops.RU_FUSED_DILATIONS
+                and c7.conv.kernel_size[0] == 7 and c1.conv.kernel_size[0] == 1 and c7.conv.out_channels == C
+                and x.shape[-1] > 6 * c7.dilation):
+            return ops.residual_unit(x, c7._packed_weight(), c7.conv.bias, c1._packed_weight(), c1.conv.bias,
+                                     dilation=c7.dilation, pad_mode=c7.pad_mode)
+        h = c7(x, elu=True)
+        return c1(h, elu=True, residual=x)
 
 
 def EncoderBlock(chan_in, chan_out, stride, cycle_dilations=(1, 3, 9), squeeze_excite=False, pad_mode="reflect"):

@@ -223,6 +223,15 @@ int alm_causal_conv1d_fwd(const float* x, const float* w, const float* bias, con
                           int w_packed, alm_stream_t stream);
 /* CausalConvTranspose1d (soundstream.py:347-360): kernel 2*stride, output trimmed to n*stride;
  * x [B,Cin,n], w [Cin,Cout,2*stride], y [B,Cout,n*stride]; polyphase form, 2 taps per input channel. */
+/*
+ * Fused ResidualUnit (soundstream.py:362-369): y = x + ELU(b1 + W1 . ELU(b7 + conv_k7,dilation(x))), causal padding
+ * as above.  One launch; the k=7 result stays in shared memory.  Weights in the packed layout ([Cin,7,Cout] and
+ * [Cin,1,Cout]); C in {32, 64, 128, 256}, dilation in {1, 3, 9} (else ALM_ERR_UNSUPPORTED: use the two conv calls).
+ * Bit-identical to alm_causal_conv1d_fwd(k7, ELU) followed by alm_causal_conv1d_fwd(k1, ELU, residual).
+ */
+int alm_residual_unit_fwd(const float* x, const float* w7_packed, const float* b7, const float* w1_packed,
+                          const float* b1, float* y, int B, int C, int T, int dilation, int pad_mode,
+                          alm_stream_t stream);
 int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
                            int n, int stride, alm_stream_t stream);
 /*
