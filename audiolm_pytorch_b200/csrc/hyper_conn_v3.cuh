@@ -44,6 +44,19 @@ __device__ __forceinline__ void slot_sum(float (&v)[N], float* mail /*[2][WPT][M
   which ^= 1;
 }
 
+// packed fp32 pairs (fma.rn.f32x2 / add / mul): the kernel is FMA-issue bound, two channels per instruction
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ void unpack4p(const uint2& u, float2* f) {  // 4 bf16 -> two (even, odd) channel pairs
+  f[0] = make_float2(bf16_lo(u.x), bf16_hi(u.x));
+  f[1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+}
+__device__ __forceinline__ uint2 pack4p(const float2* f) {
+  return make_uint2(hc2::pk(f[0].x, f[0].y), hc2::pk(f[1].x, f[1].y));
+}
+
 __device__ __forceinline__ void unpack4(const uint2& u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
 }
@@ -127,64 +140,71 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
     // ---------------- pass 1: every per-token sum in one reduction ----------------
     // red: 0 sum gl | 1 sum gl*xhat | 2+s sum gl*R_s | 6+s sum R_s | 10+s sum xhat*R_s | 14+s sum ex*R_s |
     //      18+4s+(t-1) sum dR_out[t-1]*R_s      (gl = dxn * ln_gamma, xhat = normalised branch input, ex = dbin_extra)
-    float red[NRED];
+    float2 red2[NRED];  // .x / .y: partial sums over even / odd channels (added before the reduction)
 #pragma unroll
-    for (int i = 0; i < NRED; ++i) red[i] = 0.f;
+    for (int i = 0; i < NRED; ++i) red2[i] = make_float2(0.f, 0.f);
+    const float2 rstd2 = dup2(rstd), nmr2 = dup2(-mean * rstd);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       if (act[k]) {
         const size_t o1 = (size_t)m * d + ch[k];
-        float y[4], dx[4], ex[4], lg[4], gacc[4], r[S][4];
-        unpack4(ldg8(Y + o1), y);
-        unpack4(ldg8(dxn + o1), dx);
+        float2 y[2], dx[2], ex[2], r[S][2];
+        unpack4p(ldg8(Y + o1), y);
+        unpack4p(ldg8(dxn + o1), dx);
         if (dbin_extra != nullptr) {
-          unpack4(ldg8(dbin_extra + o1), ex);
+          unpack4p(ldg8(dbin_extra + o1), ex);
         } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) ex[e] = 0.f;
+          ex[0] = ex[1] = make_float2(0.f, 0.f);
         }
-        hc2::lds4(sLn + ch[k], lg);
-        hc2::lds4(sGln + ch[k], gacc);
+        const float4 lg4 = *reinterpret_cast<const float4*>(sLn + ch[k]);
+        const float4 ga4 = *reinterpret_cast<const float4*>(sGln + ch[k]);
+        const float2 lg[2] = {make_float2(lg4.x, lg4.y), make_float2(lg4.z, lg4.w)};
+        float2 gacc[2] = {make_float2(ga4.x, ga4.y), make_float2(ga4.z, ga4.w)};
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          float rv[4];
-          unpack4(ldg8(R_in + ((size_t)m * S + s) * d + ch[k]), rv);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[s][e] = fmaf(bp[s], y[e], rv[e]);
+          float2 rv[2];
+          unpack4p(ldg8(R_in + ((size_t)m * S + s) * d + ch[k]), rv);
+          const float2 b2 = dup2(bp[s]);
+          r[s][0] = fma2(b2, y[0], rv[0]);
+          r[s][1] = fma2(b2, y[1], rv[1]);
         }
-        float gl[4], xh[4];
+        float2 gl[2], xh[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float b = 0.f;
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float2 bsum = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int s = 0; s < S; ++s) b = fmaf(alpha0[s], r[s][e], b);
-          xh[e] = (b - mean) * rstd;
-          gl[e] = dx[e] * lg[e];
-          gacc[e] = fmaf(dx[e], xh[e], gacc[e]);
-          red[0] += gl[e];
-          red[1] = fmaf(gl[e], xh[e], red[1]);
+          for (int s = 0; s < S; ++s) bsum = fma2(dup2(alpha0[s]), r[s][h2], bsum);
+          xh[h2] = fma2(bsum, rstd2, nmr2);
+          gl[h2] = mul2(dx[h2], lg[h2]);
+          gacc[h2] = fma2(dx[h2], xh[h2], gacc[h2]);
+          red2[0] = add2(red2[0], gl[h2]);
+          red2[1] = fma2(gl[h2], xh[h2], red2[1]);
         }
-        *reinterpret_cast<float4*>(sGln + ch[k]) = make_float4(gacc[0], gacc[1], gacc[2], gacc[3]);
+        *reinterpret_cast<float4*>(sGln + ch[k]) = make_float4(gacc[0].x, gacc[0].y, gacc[1].x, gacc[1].y);
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            red[2 + s] = fmaf(gl[e], r[s][e], red[2 + s]);
-            red[6 + s] += r[s][e];
-            red[10 + s] = fmaf(xh[e], r[s][e], red[10 + s]);
-            red[14 + s] = fmaf(ex[e], r[s][e], red[14 + s]);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            red2[2 + s] = fma2(gl[h2], r[s][h2], red2[2 + s]);
+            red2[6 + s] = add2(red2[6 + s], r[s][h2]);
+            red2[10 + s] = fma2(xh[h2], r[s][h2], red2[10 + s]);
+            red2[14 + s] = fma2(ex[h2], r[s][h2], red2[14 + s]);
           }
 #pragma unroll
         for (int t = 1; t < T; ++t) {
-          float dm[4];
-          unpack4(ldg8(dR_out + ((size_t)m * S + (t - 1)) * d + ch[k]), dm);
+          float2 dm[2];
+          unpack4p(ldg8(dR_out + ((size_t)m * S + (t - 1)) * d + ch[k]), dm);
 #pragma unroll
           for (int s = 0; s < S; ++s)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) red[18 + 4 * s + (t - 1)] = fmaf(dm[e], r[s][e], red[18 + 4 * s + (t - 1)]);
+            for (int h2 = 0; h2 < 2; ++h2)
+              red2[18 + 4 * s + (t - 1)] = fma2(dm[h2], r[s][h2], red2[18 + 4 * s + (t - 1)]);
         }
       }
     }
+    float red[NRED];
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) red[i] = red2[i].x + red2[i].y;
     slot_sum<NRED>(red, mail, which, w2, lane, bar_id);
     const float m1 = red[0] * inv_d, m2 = red[1] * inv_d;
     // ---------------- per-token scalars: thread s < 4 owns stream s ----------------
@@ -242,68 +262,81 @@ pre_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* __re
       *reinterpret_cast<uint4*>(WYout + (size_t)m * 8) = hc2::pack8(wy);
     }
     // ---------------- pass 2: gradients ----------------
-    float dbp[S] = {0.f, 0.f, 0.f, 0.f};
+    float2 dbp2[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) dbp2[s] = make_float2(0.f, 0.f);
+    const float2 nm1 = dup2(-m1), nm2 = dup2(-m2);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       if (act[k]) {
         const size_t o1 = (size_t)m * d + ch[k];
-        float y[4], r[S][4], dm[T][4], dy[4];
-        unpack4(ldg8(Y + o1), y);
+        float2 y[2], r[S][2], dm[T][2], dy[2];
+        unpack4p(ldg8(Y + o1), y);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          float rv[4];
-          unpack4(ldg8(R_in + ((size_t)m * S + s) * d + ch[k]), rv);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) r[s][e] = fmaf(bp[s], y[e], rv[e]);
+          float2 rv[2];
+          unpack4p(ldg8(R_in + ((size_t)m * S + s) * d + ch[k]), rv);
+          const float2 b2 = dup2(bp[s]);
+          r[s][0] = fma2(b2, y[0], rv[0]);
+          r[s][1] = fma2(b2, y[1], rv[1]);
         }
         {
-          float dx[4], ex[4], lg[4];
-          unpack4(ldg8(dxn + o1), dx);
+          float2 dx[2], ex[2];
+          unpack4p(ldg8(dxn + o1), dx);
           if (dbin_extra != nullptr) {
-            unpack4(ldg8(dbin_extra + o1), ex);
+            unpack4p(ldg8(dbin_extra + o1), ex);
           } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) ex[e] = 0.f;
+            ex[0] = ex[1] = make_float2(0.f, 0.f);
           }
-          hc2::lds4(sLn + ch[k], lg);
+          const float4 lg4 = *reinterpret_cast<const float4*>(sLn + ch[k]);
+          const float2 lg[2] = {make_float2(lg4.x, lg4.y), make_float2(lg4.z, lg4.w)};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float b = 0.f;
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float2 bsum = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int s = 0; s < S; ++s) b = fmaf(alpha0[s], r[s][e], b);
-            const float xhat = (b - mean) * rstd;
-            dm[0][e] = fmaf(rstd, fmaf(dx[e], lg[e], -m1) - xhat * m2, ex[e]);  // d(branch input)
-            dy[e] = 0.f;
+            for (int s = 0; s < S; ++s) bsum = fma2(dup2(alpha0[s]), r[s][h2], bsum);
+            const float2 xhat = fma2(bsum, rstd2, nmr2);
+            // d(branch input) = rstd * (dxn*ln_gamma - m1 - xhat*m2) + dbin_extra
+            const float2 inner = fma2(xhat, nm2, fma2(dx[h2], lg[h2], nm1));
+            dm[0][h2] = fma2(rstd2, inner, ex[h2]);
+            dy[h2] = make_float2(0.f, 0.f);
           }
         }
 #pragma unroll
-        for (int t = 1; t < T; ++t) unpack4(ldg8(dR_out + ((size_t)m * S + (t - 1)) * d + ch[k]), dm[t]);
-        float pg[6][4];
+        for (int t = 1; t < T; ++t) unpack4p(ldg8(dR_out + ((size_t)m * S + (t - 1)) * d + ch[k]), dm[t]);
+        float2 pg[6][2];
 #pragma unroll
-        for (int c6 = 0; c6 < 6; ++c6) hc2::lds4(sPg + c6 * d + ch[k], pg[c6]);
+        for (int c6 = 0; c6 < 6; ++c6) {
+          const float4 p4 = *reinterpret_cast<const float4*>(sPg + c6 * d + ch[k]);
+          pg[c6][0] = make_float2(p4.x, p4.y);
+          pg[c6][1] = make_float2(p4.z, p4.w);
+        }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           float cf[COEF];
 #pragma unroll
           for (int q = 0; q < 3; ++q) hc2::lds4(sCoef + s * COEF + q * 4, cf + q * 4);
-          cf[12] = bp[s];
-          float dr[4];
+          const float2 nkk = dup2(-cf[2 * T + 1]), bps2 = dup2(bp[s]);
+          float2 dr[2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float acc = -r[s][e] * cf[2 * T + 1];
+          for (int h2 = 0; h2 < 2; ++h2) {
+            float2 acc = mul2(r[s][h2], nkk);
 #pragma unroll
-            for (int t = 0; t < T; ++t) acc = fmaf(cf[t], dm[t][e], acc);
+            for (int t = 0; t < T; ++t) acc = fma2(dup2(cf[t]), dm[t][h2], acc);
 #pragma unroll
-            for (int c6 = 0; c6 < 6; ++c6) acc = fmaf(cf[T + c6], pg[c6][e], acc);
-            dr[e] = acc;
-            dbp[s] = fmaf(acc, y[e], dbp[s]);
-            dy[e] = fmaf(cf[12], acc, dy[e]);
+            for (int c6 = 0; c6 < 6; ++c6) acc = fma2(dup2(cf[T + c6]), pg[c6][h2], acc);
+            dr[h2] = acc;
+            dbp2[s] = fma2(acc, y[h2], dbp2[s]);
+            dy[h2] = fma2(bps2, acc, dy[h2]);
           }
-          *reinterpret_cast<uint2*>(dR_in + ((size_t)m * S + s) * d + ch[k]) = pack4(dr);
+          *reinterpret_cast<uint2*>(dR_in + ((size_t)m * S + s) * d + ch[k]) = pack4p(dr);
         }
-        *reinterpret_cast<uint2*>(dY + o1) = pack4(dy);
+        *reinterpret_cast<uint2*>(dY + o1) = pack4p(dy);
       }
     }
+    float dbp[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) dbp[s] = dbp2[s].x + dbp2[s].y;
     slot_sum<S>(dbp, mail, which, w2, lane, bar_id);
     if (lt == 0) {
 #pragma unroll
