@@ -50,8 +50,11 @@ print("| kernel class | launches | ms | TFLOP/s | % of bf16 sustained peak |")
 print("|---|---|---|---|---|")
 tot = 0.0
 for cls, (ms, work, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-    tf = work / (ms * 1e-3) / 1e12 if ms else 0
+    rate = work / (ms * 1e-3) if ms else 0
     tot += ms
-    print(f"| {cls} | {n} | {ms:.3f} | {tf:.0f} | {100 * tf / pk['tf_sustained']:.0f}% |")
+    if ops.CLASS_UNIT.get(cls) == "byte":  # HBM-bound classes: GB/s of algorithmic bytes vs the measured copy peak
+        print(f"| {cls} | {n} | {ms:.3f} | {rate / 1e9:.0f} GB/s | {100 * rate / 1e9 / pk['hbm']:.0f}% of HBM |")
+    else:
+        print(f"| {cls} | {n} | {ms:.3f} | {rate / 1e12:.0f} | {100 * rate / 1e12 / pk['tf_sustained']:.0f}% |")
 print(f"\ntimed classes total {tot:.2f} ms of {step_ms:.2f} ms step; the rest is hyper-connection / GEGLU / CE / torch glue "
       "kernels (see the ncu launch list).")
