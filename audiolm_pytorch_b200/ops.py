@@ -1,4 +1,4 @@
-"""Python faces of the C-ABI kernels (raw ops; autograd wiring lives in `functional.py`).
+"""Python faces of the C-ABI kernels (raw ops; the autograd wiring lives in transformer.py / heads.py / rel_pos.py).
 
 Every function here launches hand-written sm_100a kernels from libalm_b200.so on the current CUDA
 stream.  No function has a CPU or stock-PyTorch implementation.
