@@ -5,6 +5,11 @@ The reference reaches the same collective through accelerate -> torch DDP (train
 with 25 MB buckets and `find_unused_parameters=True`.  Here every parameter's `.grad` is a view into one
 contiguous buffer, so the whole exchange is a single NCCL all-reduce over NVLink / NVSwitch followed by
 a scale by 1/world (mean, as DDP does).  Works on CPU with gloo for the world_size-2 tests.
+
+Overlap with the backward (what DDP's bucket hooks do): `Transformer.grad_ready_hook(i)` fires when layer i's
+gradients are complete; `reduce_range_async` then starts the all-reduce of that layer's slice of the flat buffer on
+the communication stream while the earlier layers are still being differentiated, and `finish()` reduces whatever
+is left (embeddings, heads), waits and applies the 1/world scale once.
 """
 from __future__ import annotations
 
@@ -20,10 +25,13 @@ class FlatGradBucket:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, device=dev, dtype=dtype)
         off = 0
+        self._span = {}
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
+            self._span[id(p)] = (off, off + n)
             off += n
+        self._pending, self._done = [], []  # async work handles / [lo, hi) intervals already handed to the collective
 
     def zero_(self):
         self.flat.zero_()
@@ -38,6 +46,38 @@ class FlatGradBucket:
             return work
         self.flat.div_(world)
         return None
+
+    # ---- overlapped exchange ----------------------------------------------------------------------
+    def range_of(self, params):
+        """[lo, hi) of the flat buffer covered by `params` (they must be adjacent in the bucket)."""
+        spans = sorted(self._span[id(p)] for p in params if id(p) in self._span)
+        assert spans, "parameters are not part of this bucket"
+        for (_, e), (s2, _) in zip(spans, spans[1:]):
+            assert e == s2, "parameters are not contiguous in the bucket"
+        return spans[0][0], spans[-1][1]
+
+    def reduce_range_async(self, lo, hi, group=None):
+        """start the SUM all-reduce of flat[lo:hi]; the 1/world scale is applied by finish()."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or hi <= lo:
+            return
+        self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        self._done.append((lo, hi))
+
+    def finish(self, group=None):
+        """all-reduce every slice not yet handed over, wait for all of them, scale by 1/world (mean)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            self._pending, self._done = [], []
+            return
+        pos = 0
+        for lo, hi in sorted(self._done) + [(self.numel, self.numel)]:
+            if lo > pos:
+                self._pending.append(dist.all_reduce(self.flat[pos:lo], op=dist.ReduceOp.SUM, group=group,
+                                                     async_op=True))
+            pos = max(pos, hi)
+        for w in self._pending:
+            w.wait()
+        self._pending, self._done = [], []
+        self.flat.div_(dist.get_world_size(group))
 
     def grad_norm(self):
         return self.flat.norm(2)

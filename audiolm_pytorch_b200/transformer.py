@@ -290,6 +290,9 @@ class Transformer(nn.Module):
             ]))
         self.norm = LayerNorm(dim)
         self._packed = _PackedWeights()
+        # called with the layer index once that layer's parameter gradients are complete in the backward
+        # (parallel.FlatGradBucket.reduce_range_async overlaps the gradient all-reduce with the remaining layers)
+        self.grad_ready_hook = None
 
     def invalidate_weight_cache(self):
         """drop the bf16 operand copies (they are rebuilt on the next forward, as autocast re-casts weights)."""
@@ -489,6 +492,8 @@ class Transformer(nn.Module):
                 dx = ops.hc_pre_bwd(attn_hc.kernel_params(), a.norm.gamma, a_hc, g_ln_a, rec["aux_a"], dR_a, dxn_a,
                                     dbeta_a, dbin_extra=dbin_a, x_expand=S["x2"], dx_scale=self.grad_shrink_alpha,
                                     M=M, d=d)
+            if self.grad_ready_hook is not None and returned[0] is None:
+                self.grad_ready_hook(i)  # layer i's gradients are final in their `.grad` buffers (direct accumulation)
         return dx.view(b, n, d).to(S["x_dtype"]), returned
 
 

@@ -220,6 +220,14 @@ def main_ours(args):
     torch.manual_seed(1234)
     model = CoarseTransformer(**CFG).to(dev).train()
     bucket = FlatGradBucket(model.parameters())
+    overlap = world > 1 and os.environ.get("ALM_OVERLAP_ALLREDUCE") is not None
+    if overlap:
+        # optional: layer i's slice of the flat bucket is all-reduced (NCCL, its own stream) as soon as its gradients
+        # are final.  Measured at N=2: 30.50 ms/step vs 30.25 ms with ONE all-reduce after the backward (the NCCL
+        # kernels only get SMs between the persistent GEMMs and 7 small collectives cost more than one big one),
+        # so the single all-reduce stays the default (profiles/r01_bench_n2_v3_overlap_ab.txt).
+        ranges = [bucket.range_of(list(layer.parameters())) for layer in model.transformer.layers]
+        model.transformer.grad_ready_hook = lambda i: bucket.reduce_range_async(*ranges[i])
     n_params = bucket.numel
 
     sem_h, coarse_h = synth_ids(BATCH, rank)
@@ -240,7 +248,7 @@ def main_ours(args):
         n_s, n_c = sl.shape[1], cl.shape[1]
         loss = (ls * n_s + lc * n_c) / (n_s + n_c)
         loss.backward()
-        bucket.all_reduce_mean()
+        bucket.finish()  # N > 1: the layers' slices were reduced under the backward; this sends the rest and scales
         return loss
 
     def barrier():
@@ -311,7 +319,7 @@ def main_ours(args):
         "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD + (" + grad all-reduce" if world > 1 else ""),
+        "config": {"workload": WORKLOAD + ((" + grad all-reduce" + (" (overlapped with the backward)" if overlap else "")) if world > 1 else ""),
                    "global_batch": world * BATCH, "seq_len": SEQ, "parallelism": f"dp{world}", "params": n_params,
                    "l2": "working set (~9 GB of saved activations per step) far exceeds the 126 MB L2"},
         "e2e": {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s",

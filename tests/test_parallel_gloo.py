@@ -35,6 +35,13 @@ def _worker(rank, world, port, ret):
     # grads are still views of the bucket after autograd accumulated into them
     ok = ok and all(torch.equal(p.grad.view(-1), bucket.flat[o:o + p.numel()])
                     for p, o in zip(bucket.params, _offsets(bucket.params)))
+    # overlapped exchange: one slice early (as Transformer.grad_ready_hook would), the rest in finish()
+    bucket.flat.copy_(local)
+    lo, hi = bucket.range_of(list(model[2].parameters()))
+    assert (lo, hi) == (8 * 16 + 16, bucket.numel)
+    bucket.reduce_range_async(lo, hi)
+    bucket.finish()
+    ok = ok and torch.allclose(bucket.flat, expect, atol=1e-6)
     norm = bucket.clip_grad_norm_(0.5)
     ok = ok and bucket.flat.norm() <= 0.5 + 1e-4 and norm > 0
     ret[rank] = bool(ok)
