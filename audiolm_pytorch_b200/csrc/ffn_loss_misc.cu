@@ -278,160 +278,8 @@ geglu_ln_bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate
 }
 
 
-// ---- GEGLU + LN, second generation: 2 warps per row, 4 rows per CTA, named barriers only ------------------
-// (v1 above walks one row per CTA with CTA-wide barriers and is kept for inner_pad > 3072.)
-namespace gg2 {
-constexpr int ROWS = 4, THREADS = 64 * ROWS, NCH = 6;  // 64 threads x 6 chunks x 8 = 3072 columns max
-
-__device__ __forceinline__ void bar64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-template <int N>
-__device__ __forceinline__ void slot_sum(float (&v)[N], float* mail, int& which, int w2, int lane, int bar_id) {
-#pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
-  float* b = mail + which * 4;
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) b[w2 * 2 + i] = v[i];
-  }
-  bar64(bar_id);
-#pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = b[i] + b[2 + i];
-  which ^= 1;
-}
-
-__global__ void __launch_bounds__(THREADS, 2)
-fwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate_off, const float* __restrict__ gamma,
-           __nv_bfloat16* __restrict__ gn, long long ldg, float* __restrict__ stats, int M, int inner, int inner_pad) {
-  __shared__ float mailbox[ROWS * 8];
-  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
-  float* mail = mailbox + slot * 8;
-  int which = 0;
-  const int bar_id = 1 + slot;
-  for (int m = blockIdx.x * ROWS + slot; m < M; m += gridDim.x * ROWS) {
-    float g[NCH][8];
-    float s1[1] = {0.f};
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c0 = (lt + 64 * k) * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) g[k][e] = 0.f;
-      if (c0 < inner_pad) {
-        float a[8], gt[8];
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a);
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          g[k][e] = (c0 + e < inner) ? gelu_erf(gt[e]) * a[e] : 0.f;
-          s1[0] += g[k][e];
-        }
-      }
-    }
-    slot_sum<1>(s1, mail, which, w2, lane, bar_id);
-    const float mean = s1[0] / inner;
-    float s2[1] = {0.f};
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c0 = (lt + 64 * k) * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (c0 + e < inner) s2[0] = fmaf(g[k][e] - mean, g[k][e] - mean, s2[0]);
-    }
-    slot_sum<1>(s2, mail, which, w2, lane, bar_id);
-    const float rstd = rsqrtf(s2[0] / inner + 1e-5f);
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c0 = (lt + 64 * k) * 8;
-      if (c0 < inner_pad) {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (c0 + e < inner) ? (g[k][e] - mean) * rstd * __ldg(gamma + c0 + e) : 0.f;
-        *reinterpret_cast<uint4*>(gn + (size_t)m * ldg + c0) = pack8b(o);
-      }
-    }
-    if (lt == 0) {
-      stats[(size_t)m * 2] = mean;
-      stats[(size_t)m * 2 + 1] = rstd;
-    }
-  }
-}
-
-// dgamma is accumulated in a private per-slot smem row [ROWS][inner_pad] (plain RMW), flushed once per CTA
-__global__ void __launch_bounds__(THREADS, 1)
-bwd_kernel(const __nv_bfloat16* __restrict__ h, long long ldh, int gate_off, const float* __restrict__ gamma,
-           const float* __restrict__ stats, const __nv_bfloat16* __restrict__ dgn, long long ldg,
-           __nv_bfloat16* __restrict__ dh, float* __restrict__ g_gamma, int M, int inner, int inner_pad) {
-  extern __shared__ float gacc_all[];  // [ROWS][inner_pad]
-  __shared__ float mailbox[ROWS * 8];
-  for (int i = threadIdx.x; i < ROWS * inner_pad; i += blockDim.x) gacc_all[i] = 0.f;
-  __syncthreads();
-  const int slot = threadIdx.x >> 6, lt = threadIdx.x & 63, w2 = lt >> 5, lane = lt & 31;
-  float* mail = mailbox + slot * 8;
-  float* gacc = gacc_all + (size_t)slot * inner_pad;
-  int which = 0;
-  const int bar_id = 1 + slot;
-  for (int m = blockIdx.x * ROWS + slot; m < M; m += gridDim.x * ROWS) {
-    const float mean = stats[(size_t)m * 2], rstd = stats[(size_t)m * 2 + 1];
-    float a[NCH][8], gt[NCH][8], gl[NCH][8];
-    float r2[2] = {0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c0 = (lt + 64 * k) * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { a[k][e] = gt[k][e] = gl[k][e] = 0.f; }
-      if (c0 < inner_pad) {
-        float dv[8];
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + c0), a[k]);
-        unpack8b(*reinterpret_cast<const uint4*>(h + (size_t)m * ldh + gate_off + c0), gt[k]);
-        unpack8b(*reinterpret_cast<const uint4*>(dgn + (size_t)m * ldg + c0), dv);
-        float4 ga = *reinterpret_cast<float4*>(gacc + c0), gb = *reinterpret_cast<float4*>(gacc + c0 + 4);
-        float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (c0 + e < inner) {
-            const float xh = (gelu_erf(gt[k][e]) * a[k][e] - mean) * rstd;
-            gl[k][e] = dv[e] * __ldg(gamma + c0 + e);
-            gv[e] = fmaf(dv[e], xh, gv[e]);
-            r2[0] += gl[k][e];
-            r2[1] = fmaf(gl[k][e], xh, r2[1]);
-          }
-        }
-        *reinterpret_cast<float4*>(gacc + c0) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-        *reinterpret_cast<float4*>(gacc + c0 + 4) = make_float4(gv[4], gv[5], gv[6], gv[7]);
-      }
-    }
-    slot_sum<2>(r2, mail, which, w2, lane, bar_id);
-    const float m1 = r2[0] / inner, m2 = r2[1] / inner;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c0 = (lt + 64 * k) * 8;
-      if (c0 < inner_pad) {
-        float da[8], dg8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (c0 + e < inner) {
-            const float ge = gelu_erf(gt[k][e]);
-            const float xh = (ge * a[k][e] - mean) * rstd;
-            const float dg = rstd * (gl[k][e] - m1 - xh * m2);
-            da[e] = dg * ge;
-            dg8[e] = dg * a[k][e] * gelu_erf_grad(gt[k][e]);
-          } else {
-            da[e] = dg8[e] = 0.f;
-          }
-        }
-        *reinterpret_cast<uint4*>(dh + (size_t)m * ldh + c0) = pack8b(da);
-        *reinterpret_cast<uint4*>(dh + (size_t)m * ldh + gate_off + c0) = pack8b(dg8);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll
-    for (int sl = 0; sl < ROWS; ++sl) acc += gacc_all[(size_t)sl * inner_pad + i];
-    atomicAdd(g_gamma + i, acc);
-  }
-}
-}  // namespace gg2
+// (A two-warps-per-row variant of these kernels was measured slower - 0.29 vs 0.27 ms forward, 0.78 vs 0.56 ms
+// backward at C3 - and removed; the row-per-CTA layout above is the one dispatched.)
 
 // ---- cross entropy: one CTA per row -----------------------------------------------------------
 // loss_rows[r] = lse - logit[label]  (0 when label == ignore)
@@ -675,14 +523,6 @@ extern "C" int alm_geglu_ln_fwd(const void* h, int64_t ldh, int gate_off, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(M > 0 && inner > 0 && inner_pad >= inner && inner_pad % 8 == 0, ALM_ERR_ARG);
   ALM_REQUIRE(ldh % 8 == 0 && ldg % 8 == 0 && gate_off % 8 == 0, ALM_ERR_ALIGN);
-  if (false && inner_pad <= gg2::NCH * 64 * 8) {  // v2 measured slower than v1 at C3 (0.29 vs 0.27 ms): disabled
-    const int grid2 = min(ceil_div(M, gg2::ROWS), num_sms() * 2);
-    gg2::fwd_kernel<<<grid2, gg2::THREADS, 0, stream>>>((const __nv_bfloat16*)h, ldh, gate_off, gamma,
-                                                        (__nv_bfloat16*)gn, ldg, stats, M, inner, inner_pad);
-    ALM_CHECK_LAUNCH();
-    ALM_LAUNCHED(1);
-    return ALM_OK;
-  }
   const int nch = ceil_div(inner_pad / 8, FF_THREADS);
   ALM_REQUIRE(nch <= FF_MAX_CHUNKS, ALM_ERR_UNSUPPORTED);
   const int grid = min(M, num_sms() * 8);
@@ -702,22 +542,6 @@ extern "C" int alm_geglu_ln_bwd(const void* h, int64_t ldh, int gate_off, const 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(M > 0 && inner > 0 && inner_pad >= inner && inner_pad % 8 == 0, ALM_ERR_ARG);
   ALM_REQUIRE(ldh % 8 == 0 && ldg % 8 == 0 && gate_off % 8 == 0, ALM_ERR_ALIGN);
-  if (false && inner_pad <= gg2::NCH * 64 * 8) {  // v2 measured slower than v1 at C3 (0.78 vs 0.56 ms): disabled
-    const int grid2 = min(ceil_div(M, gg2::ROWS), num_sms());
-    const size_t smem = (size_t)gg2::ROWS * inner_pad * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      ALM_CUDA_OK(cudaFuncSetAttribute(gg2::bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(gg2::ROWS * gg2::NCH * 64 * 8 * sizeof(float))));
-      attr_set = true;
-    }
-    gg2::bwd_kernel<<<grid2, gg2::THREADS, smem, stream>>>((const __nv_bfloat16*)h, ldh, gate_off, gamma, stats,
-                                                           (const __nv_bfloat16*)dgn, ldg, (__nv_bfloat16*)dh,
-                                                           g_gamma, M, inner, inner_pad);
-    ALM_CHECK_LAUNCH();
-    ALM_LAUNCHED(1);
-    return ALM_OK;
-  }
   const int nch = ceil_div(inner_pad / 8, FF_THREADS);
   ALM_REQUIRE(nch <= FF_MAX_CHUNKS, ALM_ERR_UNSUPPORTED);
   auto* hp = (const __nv_bfloat16*)h;
