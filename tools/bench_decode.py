@@ -33,22 +33,24 @@ fine = FineTransformerWrapper(transformer=FineTransformer(num_coarse_quantizers=
 out = {}
 
 
-def timed(name, fn, n_tokens):
-    fn()  # warm-up (packs weights)
+def timed(name, fn, n_tokens, reps=3, count=None):
+    fn()  # warm-up (packs weights, captures the decode graphs)
     torch.cuda.synchronize()
-    _lib.reset_launch_count()
-    t0 = time.perf_counter()
-    r = fn()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out[name] = {"ms_per_token": dt * 1e3 / n_tokens, "tokens": n_tokens, "alm_launches_per_token": _lib.launch_count() / n_tokens}
+    times, r = [], None
+    for _ in range(reps):
+        _lib.reset_launch_count()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3 / (count(r) if count else n_tokens))
+    times.sort()
+    out[name] = {"ms_per_token": times[len(times) // 2], "ms_per_token_min": times[0], "ms_per_token_max": times[-1],
+                 "tokens": n_tokens, "alm_launches_per_token": _lib.launch_count() / n_tokens}
     return r
 
 
-r = timed("semantic", lambda: sem.generate(max_length=steps, batch_size=1), steps)
-if r.shape[1] < steps:  # early EOS with random weights: report per generated token
-    out["semantic"]["ms_per_token"] *= steps / max(r.shape[1], 1)
-    out["semantic"]["tokens"] = int(r.shape[1])
+# random weights may emit EOS early: time per token actually generated in each repetition
+timed("semantic", lambda: sem.generate(max_length=steps, batch_size=1), steps, count=lambda r: max(int(r.shape[1]), 1))
 sem_ids = torch.randint(0, 500, (1, 500), device=dev)
 c = timed("coarse", lambda: coarse.generate(semantic_token_ids=sem_ids, max_time_steps=steps // 3), steps // 3 * 3)
 c = c.clamp(min=0)
