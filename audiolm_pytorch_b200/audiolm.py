@@ -356,7 +356,9 @@ def _cached_engine(owner, stack, batch, max_len, filter_thres, temperature, *, e
     graphs hold pointers to the packed bf16 weight copies of the current parameter versions)."""
     ver = sum(p._version for p in owner.parameters())
     max_len = -(-max_len // 256) * 256  # fewer distinct cache sizes -> fewer graph captures
-    key = (batch, max_len, float(filter_thres), float(temperature), ver, str(stack.norm.gamma.device))
+    # the graphs hold raw pointers into the packed bf16 weight copies: rebuild after invalidate_weight_cache() too
+    gens = (stack._packed.generation, owner.transformer._heads._pk.generation)
+    key = (batch, max_len, float(filter_thres), float(temperature), ver, gens, str(stack.norm.gamma.device))
     eng = getattr(owner, "_engine", None)
     if eng is None or eng[0] != key:
         dec = TokenDecoder(StackDecoder(stack, batch, max_len), embed_fn, logits_fn, filter_thres=filter_thres,

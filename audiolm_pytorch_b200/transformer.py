@@ -151,9 +151,11 @@ class _PackedWeights:
 
     def __init__(self):
         self._cache = {}
+        self.generation = 0  # bumped by clear(): captured CUDA graphs hold raw pointers into these copies
 
     def clear(self):
         self._cache.clear()
+        self.generation += 1
 
     def get(self, key, params, build):
         ver = tuple((p.data_ptr(), p._version) for p in params)
