@@ -101,3 +101,41 @@ def test_split_k_heuristic_bounds():
     for (M, N, K) in [(512, 1024, 32768), (128, 1024, 32768), (5460, 1024, 32768), (1024, 2730, 32768), (64, 64, 64)]:
         s = best_split_k(M, N, K)
         assert 1 <= s <= max(1, -(-K // 64))
+
+
+def test_kernel_bias_layout_helper():
+    """as_kernel_bias: any [h, i, j] bias becomes an fp32 tensor whose row stride is a multiple of 4 elements,
+    without a copy when the caller already holds the padded buffer (rel_pos.gather_bias slices it)."""
+    from audiolm_pytorch_b200.rel_pos import as_kernel_bias
+
+    b = torch.randn(2, 5, 7)
+    k = as_kernel_bias(b)
+    assert k.shape == (2, 5, 8) and k.is_contiguous() and torch.equal(k[..., :7], b) and (k[..., 7] == 0).all()
+    padded = torch.randn(2, 5, 8)
+    view = padded[..., :7]
+    assert as_kernel_bias(view).data_ptr() == padded.data_ptr()   # the padded base is reused
+    full = torch.randn(2, 4, 12)
+    assert as_kernel_bias(full) is full
+
+
+def test_tile_rows_equals_modulo_indexing():
+    from audiolm_pytorch_b200.audiolm import _tile_rows
+
+    w = torch.randn(3, 6, requires_grad=True)
+    for n in (0, 1, 3, 7, 12):
+        idx = torch.arange(n) % 3
+        assert torch.equal(_tile_rows(w, n), w[idx])
+    _tile_rows(w, 7).sum().backward()
+    assert torch.equal(w.grad, torch.tensor([[3.0] * 6, [2.0] * 6, [2.0] * 6]))
+
+
+def test_flat_bucket_ranges():
+    from audiolm_pytorch_b200.parallel import FlatGradBucket
+
+    m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    b = FlatGradBucket(m.parameters())
+    assert b.range_of(list(m[0].parameters())) == (0, 15) and b.range_of(list(m[1].parameters())) == (15, 23)
+    with pytest.raises(AssertionError):
+        b.range_of([m[0].weight, m[1].weight])   # not adjacent in the bucket
+    b.reduce_range_async(0, 15)                  # no process group: no-op
+    b.finish()
