@@ -4,8 +4,11 @@
 //
 // One CTA = (batch b, head h, 128 queries).  Q K^T and P V run on tcgen05 with fp32 accumulators in
 // TMEM; Q/K/V tiles arrive by TMA into 128-B-swizzled smem; the softmax is an online (flash) softmax
-// held in registers by 128 threads (thread == query row == TMEM lane).
-//   warps 0-3 : softmax / rescale / output          warp 4 : TMA producer      warp 5 : UMMA issuer
+// held in registers by 256 threads: two warps per TMEM lane quadrant, each thread owns one query row and
+// half of the key columns of a tile (the row maximum is taken over all 128 columns by both).
+//   warps 0-7 : softmax / rescale / output          warp 8 : TMA producer      warp 9 : UMMA issuer
+// An optional additive score bias [h, n_q, n_k] (flash_attn=False path, attend.py:122-124) is added in the
+// softmax warps; tiles that lie fully below the causal diagonal take a predicate-free path.
 // TMEM: S[128x128] at columns 0..127, (P V)[128x64] at columns 128..191 (256 columns allocated so two
 // CTAs can be resident per SM and overlap each other's softmax and MMA phases).
 #include "alm_common.cuh"
