@@ -39,8 +39,19 @@ def append_eos_id(ids, eos_id):
 
 
 def batch_unique_consecutive(t, pad_value=0.0):
-    rows = [torch.unique_consecutive(r) for r in t.unbind(0)]
-    return nn.utils.rnn.pad_sequence(rows, batch_first=True, padding_value=pad_value)
+    """per-row torch.unique_consecutive + pad_sequence (audiolm_pytorch.py:162-164) without the per-row host loop:
+    keep[i] = t[i] != t[i-1], destination column = running count of kept elements, one scatter.  The only host
+    round-trip left is the padded width (the output shape depends on the data)."""
+    b, n = t.shape
+    if n == 0:
+        return t
+    keep = torch.ones_like(t, dtype=torch.bool)
+    keep[:, 1:] = t[:, 1:] != t[:, :-1]
+    dest = keep.cumsum(dim=-1) - 1                       # column of each kept element
+    width = int(keep.sum(dim=-1).max())
+    out = torch.full((b, width + 1), pad_value, dtype=t.dtype, device=t.device)
+    out.scatter_(1, torch.where(keep, dest, torch.full_like(dest, width)), t)  # dropped elements land in a spare column
+    return out[:, :width]
 
 
 def get_embeds(embeddings: nn.Embedding, codes, pad_id=-1, return_mask=False, mask_pad_pos_to=0):
@@ -354,9 +365,11 @@ def _eval_no_grad(fn):
 def _cached_engine(owner, stack, batch, max_len, filter_thres, temperature, *, embed_fn, logits_fn):
     """one TokenDecoder (static KV cache + captured graphs) per wrapper, rebuilt when shapes or weights change (the
     graphs hold pointers to the packed bf16 weight copies of the current parameter versions)."""
-    ver = sum(p._version for p in owner.parameters())
+    # the captured graphs hold raw pointers to the fp32 parameters and to their packed bf16 copies: key on storage
+    # address AND version of every parameter (`p.data = ...`, load_state_dict(assign=True), .to(...) change the
+    # address without bumping the version)
+    ver = hash(tuple((p.data_ptr(), p._version) for p in owner.parameters()))
     max_len = -(-max_len // 256) * 256  # fewer distinct cache sizes -> fewer graph captures
-    # the graphs hold raw pointers into the packed bf16 weight copies: rebuild after invalidate_weight_cache() too
     gens = (stack._packed.generation, owner.transformer._heads._pk.generation)
     key = (batch, max_len, float(filter_thres), float(temperature), ver, gens, str(stack.norm.gamma.device))
     eng = getattr(owner, "_engine", None)

@@ -209,4 +209,53 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---------------------------------------------------------------------------------------------
+// additions for the codec tensor-core kernels (codec_tc.cu)
+// ---------------------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, both addresses 16-B aligned)
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Shared-memory matrix descriptor WITHOUT swizzle (layout type 0, "interleave"), K-major operand:
+//   core matrix = 8 rows x 16 B stored contiguously (128 B); SBO = byte distance between 8-row groups along M/N,
+//   LBO = byte distance between the two core matrices of one K=16 step along K.
+// With SBO = 128 every row sits 16 B after the previous one, so the start address may point at ANY row (16-B aligned):
+// that is what lets one staged activation tile serve all 7 taps of a dilated conv by shifting the start row.
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A operand (128 lanes x K bf16, two per 32-bit column) read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM, 32 lanes x 16 consecutive 32-bit columns (thread i writes lane base_lane + i)
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// fp32 -> (hi, lo) bf16 split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
 }  // namespace alm

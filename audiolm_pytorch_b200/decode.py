@@ -42,6 +42,7 @@ class StackDecoder:
         self.len = torch.zeros(1, device=dev, dtype=torch.int32)
         # key mask (1 = attend): a STATIC buffer so that captured graphs keep pointing at it; all ones by default
         self.mask = torch.ones(batch, max_len, device=dev, dtype=torch.uint8)
+        self.host_len = 0  # host mirror of `len` (graph replays advance it too): a full cache is an error, not a drop
 
     def load_cache(self, kv):
         """kv: [depth, 2, b, n, 64] as returned by Transformer(..., return_kv_cache=True)"""
@@ -50,6 +51,7 @@ class StackDecoder:
         self.kc[:, :, :n] = kv[:, 0].to(bf16)
         self.vc[:, :, :n] = kv[:, 1].to(bf16)
         self.len.fill_(n)
+        self.host_len = n
 
     def set_key_mask(self, mask=None):
         """mask: bool [b, n] (True = attend) or None; positions past n (tokens still to be generated) are attended"""
@@ -144,6 +146,10 @@ class TokenDecoder:
 
     def advance(self, key=0):
         """consume self.tok (the token sampled last), append it to the cache, sample the next one into self.tok"""
+        st = self.stack
+        if st.host_len >= st.max_len:
+            raise ops._lib.AlmError(f"decode KV cache is full ({st.max_len} positions); build the engine with a larger max_len")
+        st.host_len += 1
         if not self.use_graph:
             return self._step(key)
         g = self._graphs.get(key)

@@ -64,7 +64,10 @@ class _LinearPacked(torch.autograd.Function):
         x = x.to(bf16).contiguous()
         y = ops.gemm(x, w_packed[:V], out_dtype=f32,
                      bias=None if bias is None else bias.detach().float().contiguous())
-        ctx.save_for_backward(x, w_packed)
+        ctx.save_for_backward(x)
+        # plain attribute, not save_for_backward: the packed copy may have been built under generate()'s
+        # torch.inference_mode() and inference tensors cannot be saved for backward
+        ctx.w_packed = w_packed
         ctx.has_bias = bias is not None
         ctx.V = V
         ctx.d = weight.shape[1]
@@ -72,7 +75,8 @@ class _LinearPacked(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, w_packed = ctx.saved_tensors
+        (x,) = ctx.saved_tensors
+        w_packed = ctx.w_packed
         V, d = ctx.V, ctx.d
         dyp = ops.cast_pad(dy.contiguous(), _pad8(V))                    # bf16 [R, pad8(V)], zero tail
         dx = ops.gemm(dyp, w_packed, b_mn=True)[:, :d]                   # contraction over pad8(V) rows

@@ -33,14 +33,42 @@ class FlatGradBucket:
             off += n
         self._pending, self._done = [], []  # async work handles / [lo, hi) intervals already handed to the collective
 
+    def attach(self, module):
+        """let every `Transformer` stack inside `module` accumulate its parameter gradients straight into this
+        bucket (no per-parameter temporaries; parameter hooks do not fire for those parameters)."""
+        from .transformer import Transformer
+
+        for m in module.modules():
+            if isinstance(m, Transformer):
+                m.accumulate_into_grad = True
+        return self
+
     def zero_(self):
+        """use this instead of `optimizer.zero_grad()` (whose default set_to_none=True detaches the views)"""
+        self.sync_views()
         self.flat.zero_()
+
+    def sync_views(self):
+        """re-establish `p.grad is a view of self.flat`.  `optimizer.zero_grad(set_to_none=True)` (the torch default)
+        or an assignment to `p.grad` detaches a parameter from the bucket; its gradient is then copied in and the
+        view restored, so the collective never reduces a stale buffer."""
+        for p in self.params:
+            lo, hi = self._span[id(p)]
+            view = self.flat[lo:hi].view_as(p)
+            g = p.grad
+            if g is None:
+                view.zero_()
+                p.grad = view
+            elif g.data_ptr() != view.data_ptr() or g.dtype != self.flat.dtype or not g.is_contiguous():
+                view.copy_(g)
+                p.grad = view
 
     def all_reduce_mean(self, group=None, async_op=False):
         """sum over ranks then divide by world size (DDP semantics).  Returns the work handle if async."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         world = dist.get_world_size(group)
+        self.sync_views()
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if async_op:
             return work
@@ -68,6 +96,8 @@ class FlatGradBucket:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             self._pending, self._done = [], []
             return
+        if not self._done:
+            self.sync_views()
         pos = 0
         for lo, hi in sorted(self._done) + [(self.numel, self.numel)]:
             if lo > pos:
@@ -80,6 +110,7 @@ class FlatGradBucket:
         self.flat.div_(dist.get_world_size(group))
 
     def grad_norm(self):
+        self.sync_views()
         return self.flat.norm(2)
 
     def clip_grad_norm_(self, max_norm):

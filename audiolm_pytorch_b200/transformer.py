@@ -162,7 +162,9 @@ class _PackedWeights:
         hit = self._cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        with torch.no_grad():
+        # inference_mode(False): a copy first built inside generate() (torch.inference_mode) must stay usable by the
+        # next training forward
+        with torch.inference_mode(False), torch.no_grad():
             val = build()
         self._cache[key] = (ver, val)
         return val
@@ -230,14 +232,18 @@ class _StackFn(torch.autograd.Function):
         return (None, dx, None, dbias, *grads)
 
 
-def _grad_targets(params):
+def _grad_targets(params, direct_ok=False):
     """Where the backward accumulates parameter gradients.
 
-    If every parameter already owns a contiguous fp32 `.grad` (e.g. views of parallel.FlatGradBucket), the kernels
-    accumulate straight into it (wgrad GEMMs in accumulate mode, atomics for the small tensors) and autograd is
-    handed `None` — no temporaries, no 130 `grad += tmp` launches.  Otherwise fresh zero buffers (one flat
-    allocation, one memset) are returned to autograd."""
-    direct = all(p.grad is not None and p.grad.dtype == f32 and p.grad.is_contiguous() for p in params)
+    Default: fresh zero buffers (one flat allocation, one memset) are returned to autograd, so AccumulateGrad,
+    parameter hooks (torch DDP / accelerate reducers), `torch.autograd.grad` and optimizer-in-backward all see
+    ordinary gradients.
+
+    Opt-in (`Transformer.accumulate_into_grad = True`, set by `parallel.FlatGradBucket.attach`): if every parameter
+    owns a contiguous fp32 `.grad`, the kernels accumulate straight into it (wgrad GEMMs in accumulate mode, atomics
+    for the small tensors) and autograd is handed `None` — no temporaries, no 130 `grad += tmp` launches.  In that
+    mode parameter hooks do NOT fire for the stack's parameters; the bucket's own all-reduce replaces them."""
+    direct = direct_ok and all(p.grad is not None and p.grad.dtype == f32 and p.grad.is_contiguous() for p in params)
     if direct:
         return [p.grad for p in params], [None] * len(params)
     total = sum(p.numel() for p in params)
@@ -295,6 +301,9 @@ class Transformer(nn.Module):
         # called with the layer index once that layer's parameter gradients are complete in the backward
         # (parallel.FlatGradBucket.reduce_range_async overlaps the gradient all-reduce with the remaining layers)
         self.grad_ready_hook = None
+        # opt-in direct accumulation into existing `.grad` buffers (see _grad_targets); off by default so that torch
+        # DDP / accelerate hooks keep working
+        self.accumulate_into_grad = False
 
     def invalidate_weight_cache(self):
         """drop the bf16 operand copies (they are rebuilt on the next forward, as autocast re-casts weights)."""
@@ -427,7 +436,7 @@ class Transformer(nn.Module):
         L = S["L"]
         dout = dout.reshape(M, d).to(bf16).contiguous()
         params = self._param_list()
-        grads, returned = _grad_targets(params)
+        grads, returned = _grad_targets(params, self.accumulate_into_grad)
         PL = self.PER_LAYER
         nk = len(HC_KEYS)
 
@@ -562,7 +571,7 @@ class Transformer(nn.Module):
         L = S["L"]
         dout = dout.reshape(M, d).to(bf16).contiguous()
         params = self._param_list()
-        grads, returned = _grad_targets(params)
+        grads, returned = _grad_targets(params, self.accumulate_into_grad)
         dr, dr_b = ops.resid_ln_bwd(S["r_last"], self.norm.gamma, S["st_last"], None, dout, None, grads[-1])
         dv_first = None
         for i in reversed(range(self.depth)):

@@ -4,11 +4,15 @@
     python bench.py --gpus N --steps K --warmup W             # our CUDA path (one rank per GPU via torchrun)
     python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
 
-One step = forward of CoarseTransformer(dim 1024, depth 6, heads 8, 4 hyper-connection streams, flash
-path) on a [16, 2048]-token batch (372 semantic + 1674 coarse ids + 2 start tokens), the two cross
-entropies of CoarseTransformerWrapper.forward (audiolm_pytorch.py:1826-1854), backward to every
-parameter, and (N > 1) the flat-bucket gradient all-reduce.  Synthetic ids, random-init weights.
-Prints ONE JSON line (rank 0).
+One step = what CoarseTransformerTrainer.train_step runs (trainer.py:1242-1252): the training wrapper
+`CoarseTransformerWrapper.forward(semantic_token_ids, coarse_token_ids, return_loss=True)` with its defaults
+(unique_consecutive=True, mask_prob=0.15: EOS handling, the key-padding mask it ALWAYS passes and the forgetful
+causal mask, audiolm_pytorch.py:1742-1854) around CoarseTransformer(dim 1024, depth 6, heads 8, 4 hyper-connection
+streams, flash path) on a batch of 16 sequences of 2048 positions (371 semantic ids + EOS, 558 frames x 3 coarse
+ids, 2 start tokens), backward to every parameter, and (N > 1) the flat-bucket gradient all-reduce.
+`variants.direct_causal` times the bare transformer without any key mask (SURVEY 8(d) variant a) for comparison.
+At N=1 the line also carries the other BASELINE.json configs (C1 codec, C2, C4, C5) as extra keys.
+Synthetic ids, random-init weights.  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -28,8 +32,9 @@ sys.path.insert(0, str(ROOT))
 
 CFG = dict(num_semantic_tokens=500, codebook_size=1024, num_coarse_quantizers=3, dim=1024, depth=6, heads=8,
            flash_attn=True)
-BATCH, N_SEM, N_COARSE = 16, 372, 1674  # 1 + 372 + 1 + 1674 = 2048 positions
+BATCH, N_SEM, N_COARSE = 16, 372, 1674  # direct variant: 1 + 372 + 1 + 1674 = 2048 positions
 SEQ = 1 + N_SEM + 1 + N_COARSE
+W_SEM, W_FRAMES = 371, 558  # wrapper path: 1 + (371 + EOS) + 1 + (558*3 + EOS - 1) = 2048 positions
 METRIC = "CoarseTransformer tokens/sec fwd+bwd seq2048"
 
 
@@ -38,6 +43,24 @@ def synth_ids(batch, seed):
     sem = torch.randint(0, CFG["num_semantic_tokens"], (batch, N_SEM), generator=g)
     coarse = torch.randint(0, CFG["codebook_size"], (batch, N_COARSE), generator=g)
     return sem, coarse
+
+
+def synth_wrapper_ids(batch, seed):
+    """ids for the wrapper path; no two equal neighbours among the semantic ids, so unique_consecutive=True (the wrapper
+    default) leaves every row at full length and the step always covers exactly 2048 positions per sequence"""
+    g = torch.Generator().manual_seed(1000 + seed)
+    sem = torch.randint(0, CFG["num_semantic_tokens"], (batch, W_SEM), generator=g)
+    for i in range(1, W_SEM):
+        same = sem[:, i] == sem[:, i - 1]
+        sem[:, i] = torch.where(same, (sem[:, i] + 1) % CFG["num_semantic_tokens"], sem[:, i])
+    coarse = torch.randint(0, CFG["codebook_size"], (batch, W_FRAMES, CFG["num_coarse_quantizers"]), generator=g)
+    return sem, coarse
+
+
+class _CodecStub:
+    """the wrapper constructors read these two attributes of the codec; the codec itself is benchmarked separately"""
+    rq_groups = 1
+    num_quantizers = 8
 
 
 def peaks():
@@ -98,17 +121,22 @@ def cpu_step_fn(batch):
     model = CoarseTransformer(**CFG)
     state = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
     del model
-    sem, coarse = synth_ids(batch, 0)
-    coarse_labels = torch.cat((coarse, torch.full((batch, 1), CFG["codebook_size"])), dim=1)
-    sem_labels = sem
+    # the wrapper's arithmetic (audiolm_pytorch.py:1785-1854) restated over the oracle: EOS appended to both id
+    # streams, semantic EOS masked as a key, forgetful causal mask, the two cross entropies mixed by logit count
+    sem, coarse = synth_wrapper_ids(batch, 0)
+    sem_l = torch.cat((sem, torch.full((batch, 1), CFG["num_semantic_tokens"])), dim=1)
+    co_l = torch.cat((coarse.reshape(batch, -1), torch.full((batch, 1), CFG["codebook_size"])), dim=1)
+    keep = torch.nn.functional.pad(sem_l != CFG["num_semantic_tokens"], (1, co_l.shape[1]), value=True)
     hk = dict(heads=CFG["heads"], depth=CFG["depth"], codebook_size=CFG["codebook_size"],
               num_coarse_quantizers=CFG["num_coarse_quantizers"])
 
     def step():
         for v in state.values():
             v.grad = None
-        (sl, cl), _ = ot.coarse_forward(state, sem, coarse, **hk)
-        loss = ot.coarse_wrapper_loss(sl, cl, sem_labels, coarse_labels)
+        mask = keep & ot.fcm_mask(tuple(keep.shape), 0.15)
+        (sl, cl), _ = ot.coarse_forward(state, sem_l.masked_fill(sem_l == CFG["num_semantic_tokens"], 0), co_l[:, :-1],
+                                        self_attn_mask=mask, **hk)
+        loss = ot.coarse_wrapper_loss(sl, cl, sem_l, co_l)
         loss.backward()
         return float(loss.detach())
 
@@ -129,8 +157,9 @@ def run_cpu(steps, warmup, batch=1):
     return batch * SEQ * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
-WORKLOAD = ("C3 CoarseTransformer d1024 L6 h8 4-stream hyper-connections, flash path, "
-            "batch 16/GPU x seq 2048, fwd + CE + bwd")
+WORKLOAD = ("C3 CoarseTransformerWrapper.forward(return_loss=True) [key mask + FCM mask, wrapper defaults] around "
+            "CoarseTransformer d1024 L6 h8 4-stream hyper-connections, flash path, batch 16/GPU x seq 2048, "
+            "fwd + CE + bwd")
 
 
 def emit(line):
@@ -158,8 +187,25 @@ def main_reference(args):
 # ------------------------------------------------------------------------------------------------
 # second half of BASELINE.json's metric: SoundStream frames/s encode (config C1 shapes, batch of clips)
 # ------------------------------------------------------------------------------------------------
-def codec_encode_bench(dev, clips=32, iters=5):
-    """encoder conv stack + 8-stage RVQ on `clips` x 2 s @ 24 kHz (48000 samples -> 150 frames each)."""
+ENC_BYTES_PER_CLIP = 133.8e6  # sum over encoder layers of (C_in T_in + C_out T_out) * 4 B, fused RU = 1 layer
+
+
+def _timed_cuda(fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def codec_bench(dev, clips=32, iters=5):
+    """C1: encoder conv stack + 8-stage RVQ (and the decoder) on `clips` x 2 s @ 24 kHz (48000 samples -> 150 frames)."""
+    from audiolm_pytorch_b200 import ops
     from audiolm_pytorch_b200.soundstream import SoundStream
 
     torch.manual_seed(7)
@@ -170,31 +216,133 @@ def codec_encode_bench(dev, clips=32, iters=5):
             layer._codebook.initted.fill_(True)
     ss = ss.to(dev).eval()
     wave = torch.randn(clips, 48000, device=dev)
+    pk = peaks()
     with torch.no_grad():
-        for _ in range(2):
-            ss(wave, return_encoded=True)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            ss(wave, return_encoded=True)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / iters
-        from audiolm_pytorch_b200 import ops
+        ms = _timed_cuda(lambda: ss(wave, return_encoded=True), iters)
+        _, idx, _ = ss(wave, return_encoded=True)
+        ms_dec = _timed_cuda(lambda: ss.decode_from_codebook_indices(idx), iters)
         ops.profile_start()
         ss(wave, return_encoded=True)
         prof = ops.profile_stop()
     frames = clips * 150
-    kern = {cls: {"ms_per_call": ms_, "launches": n_, "tflops_fp32": work / (ms_ * 1e-3) / 1e12 if ms_ else 0.0}
+    kern = {cls: {"ms_per_call": ms_, "launches": n_,
+                  ("gbps" if ops.CLASS_UNIT.get(cls) == "byte" else "tflops"): work / (ms_ * 1e-3) / (1e9 if ops.CLASS_UNIT.get(cls) == "byte" else 1e12) if ms_ else 0.0}
             for cls, (ms_, work, n_) in prof.items()}
-    conv = kern.get("causal_conv1d", {})
+    conv_ms = sum(v["ms_per_call"] for k, v in kern.items() if not k.startswith("rvq"))
+    enc_gbps = ENC_BYTES_PER_CLIP * clips / (conv_ms * 1e-3) / 1e9 if conv_ms else 0.0
     return {"metric": "SoundStream frames/sec encode", "value": frames / (ms * 1e-3), "unit": "frames/s",
             "ms_per_call": ms, "clips": clips, "samples_per_clip": 48000, "kernels": kern,
-            # fp32 FMA peak of the part: SMs x 128 lanes x 2 FLOP x SM clock
-            "conv_frac_of_fp32_fma_peak": conv.get("tflops_fp32", 0.0) / (148 * 128 * 2 * 1.965e9 / 1e12),
-            "note": "fp32 CUDA-core convs + RVQ search (bit-exact code indices vs the fp32 oracle): FMA-bound, not "
-                    "HBM-bound (133.8 MB algorithmic I/O per clip would take 21 us at the measured HBM peak)"}
+            "encoder_convs": {"ms": conv_ms, "algorithmic_gbps": enc_gbps, "frac_of_hbm_peak": enc_gbps / pk["hbm"],
+                              "algorithmic_bytes": ENC_BYTES_PER_CLIP * clips},
+            "decode": {"frames_per_s": frames / (ms_dec * 1e-3), "ms_per_call": ms_dec}}
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (extra keys of the N=1 line)
+# ------------------------------------------------------------------------------------------------
+def _no_repeat(ids, vocab):
+    for i in range(1, ids.shape[1]):
+        same = ids[:, i] == ids[:, i - 1]
+        ids[:, i] = torch.where(same, (ids[:, i] + 1) % vocab, ids[:, i])
+    return ids
+
+
+def _train_bench(wrapper, model, call, positions, steps, dev):
+    from audiolm_pytorch_b200.parallel import FlatGradBucket
+
+    bucket = FlatGradBucket(model.parameters()).attach(model)
+
+    def step():
+        bucket.zero_()
+        model.transformer.invalidate_weight_cache()
+        model._heads.clear()
+        call(wrapper).backward()
+
+    ms = _timed_cuda(step, steps, warm=3)
+    return {"tokens_per_s": positions / (ms * 1e-3), "ms_per_step": ms, "positions_per_step": positions}
+
+
+def config_c2(dev, steps=5):
+    """C2: SemanticTransformerWrapper.forward(return_loss=True), batch 8 x 1024 positions (wrapper defaults)."""
+    from audiolm_pytorch_b200 import SemanticTransformer, SemanticTransformerWrapper
+
+    torch.manual_seed(2)
+    m = SemanticTransformer(num_semantic_tokens=500, dim=1024, depth=6, heads=8, flash_attn=True).to(dev)
+    w = SemanticTransformerWrapper(transformer=m).train()
+    ids = _no_repeat(torch.randint(0, 500, (8, 1023)), 500).to(dev)
+    return _train_bench(w, m, lambda w_: w_(semantic_token_ids=ids, return_loss=True), 8 * 1024, steps, dev)
+
+
+def config_c4(dev, steps=5):
+    """C4: FineTransformerWrapper.forward(return_loss=True), batch 16 x (1 + 768 + 1 + 1279 = 2049) positions."""
+    from audiolm_pytorch_b200 import FineTransformer, FineTransformerWrapper
+
+    torch.manual_seed(4)
+    m = FineTransformer(num_coarse_quantizers=3, num_fine_quantizers=5, codebook_size=1024, dim=1024, depth=6, heads=8,
+                        flash_attn=True).to(dev)
+    w = FineTransformerWrapper(transformer=m, codec=_CodecStub()).train()
+    coarse = torch.randint(0, 1024, (16, 256, 3), device=dev)
+    fine = torch.randint(0, 1024, (16, 256, 5), device=dev)
+    return _train_bench(w, m, lambda w_: w_(coarse_token_ids=coarse, fine_token_ids=fine, return_loss=True),
+                        16 * 2049, steps, dev)
+
+
+def config_c5(dev, window=120):
+    """C5: KV-cache decode latency, batch 1: ms per generated token of the three generate() loops (wall clock around
+    the public call, one warm-up call that also captures the decode graphs), median of 3."""
+    from audiolm_pytorch_b200 import (CoarseTransformer, CoarseTransformerWrapper, FineTransformer,
+                                      FineTransformerWrapper, SemanticTransformer, SemanticTransformerWrapper)
+
+    torch.manual_seed(5)
+    kw = dict(dim=1024, depth=6, heads=8, flash_attn=True)
+    out = {}
+
+    def timed(name, fn, count):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3 / max(count(r), 1))
+        out[name] = {"ms_per_token": sorted(ts)[1]}
+
+    sem = SemanticTransformerWrapper(transformer=SemanticTransformer(num_semantic_tokens=500, **kw).to(dev),
+                                     unique_consecutive=False)
+    timed("semantic", lambda: sem.generate(max_length=window, batch_size=1), lambda r: int(r.shape[1]))
+    del sem
+    coarse = CoarseTransformerWrapper(transformer=CoarseTransformer(num_semantic_tokens=500, codebook_size=1024,
+                                                                    num_coarse_quantizers=3, **kw).to(dev),
+                                      codec=_CodecStub(), unique_consecutive=False)
+    sem_ids = torch.randint(0, 500, (1, 500), device=dev)
+    timed("coarse", lambda: coarse.generate(semantic_token_ids=sem_ids, max_time_steps=window // 3),
+          lambda r: window // 3 * 3)
+    del coarse
+    fine = FineTransformerWrapper(transformer=FineTransformer(num_coarse_quantizers=3, num_fine_quantizers=5,
+                                                              codebook_size=1024, **kw).to(dev), codec=_CodecStub())
+    c_ids = torch.randint(0, 1024, (1, window // 5, 3), device=dev)
+    timed("fine", lambda: fine.generate(coarse_token_ids=c_ids), lambda r: window // 5 * 5)
+    out["window_tokens"] = window
+    return out
+
+
+def gemm_traffic_from_profile():
+    """DRAM bytes (read + write) per GEMM launch from the committed ncu capture of this command's step
+    (`--metrics dram__bytes_read.sum,dram__bytes_write.sum`): parsed at run time from profiles/, newest round first."""
+    import csv
+    for name in ("r02_ncu_gemm_dram_bytes_per_launch_one_step.csv", "r01_ncu_gemm_dram_bytes_per_launch_one_step.csv"):
+        f = ROOT / "profiles" / name
+        if not f.exists():
+            continue
+        total, ids = 0.0, set()
+        for row in csv.reader(open(f, errors="replace")):
+            if len(row) >= 15 and row[0].isdigit() and "gemm_bf16_tcgen05" in row[4] and row[12].startswith("dram__bytes"):
+                total += float(row[14])
+                ids.add(row[0])
+        if ids:
+            return total / len(ids), f"profiles/{name} ({len(ids)} launches)"
+    return None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,7 +352,7 @@ def main_ours(args):
     import torch.distributed as dist
 
     from audiolm_pytorch_b200 import _lib, ops
-    from audiolm_pytorch_b200.audiolm import CoarseTransformer
+    from audiolm_pytorch_b200.audiolm import CoarseTransformer, CoarseTransformerWrapper
     from audiolm_pytorch_b200.heads import cross_entropy
     from audiolm_pytorch_b200.parallel import FlatGradBucket
 
@@ -219,36 +367,46 @@ def main_ours(args):
 
     torch.manual_seed(1234)
     model = CoarseTransformer(**CFG).to(dev).train()
-    bucket = FlatGradBucket(model.parameters())
+    wrapper = CoarseTransformerWrapper(transformer=model, codec=_CodecStub()).train()  # reference defaults
+    bucket = FlatGradBucket(model.parameters()).attach(model)
     overlap = world > 1 and os.environ.get("ALM_OVERLAP_ALLREDUCE") is not None
     if overlap:
         # optional: layer i's slice of the flat bucket is all-reduced (NCCL, its own stream) as soon as its gradients
-        # are final.  Measured at N=2: 30.50 ms/step vs 30.25 ms with ONE all-reduce after the backward (the NCCL
-        # kernels only get SMs between the persistent GEMMs and 7 small collectives cost more than one big one),
-        # so the single all-reduce stays the default (profiles/r01_bench_n2_v3_overlap_ab.txt).
+        # are final (measured at N=2 in round 1: no gain over ONE all-reduce after the backward)
         ranges = [bucket.range_of(list(layer.parameters())) for layer in model.transformer.layers]
         model.transformer.grad_ready_hook = lambda i: bucket.reduce_range_async(*ranges[i])
     n_params = bucket.numel
 
-    sem_h, coarse_h = synth_ids(BATCH, rank)
-    sem_pin, coarse_pin = sem_h.pin_memory(), coarse_h.pin_memory()
-    sem_d, coarse_d = sem_h.to(dev), coarse_h.to(dev)
+    wsem_h, wco_h = synth_wrapper_ids(BATCH, rank)
+    wsem_pin, wco_pin = wsem_h.pin_memory(), wco_h.pin_memory()
+    wsem_d, wco_d = wsem_h.to(dev), wco_h.to(dev)
+    sem_d, coarse_d = (t.to(dev) for t in synth_ids(BATCH, rank))
     eos = torch.full((BATCH, 1), CFG["codebook_size"], device=dev)
 
-    def step(sem, coarse):
+    def prep():
         bucket.zero_()
         # a real training step sees new weights every iteration: rebuild the bf16 operand copies inside the
         # timed region (what bf16 autocast does at every Linear) instead of reusing last step's cache
         model.transformer.invalidate_weight_cache()
         model._heads.clear()
-        coarse_labels = torch.cat((coarse, eos), dim=1)
-        sl, cl = model(semantic_token_ids=sem, coarse_token_ids=coarse)
-        ls = cross_entropy(sl, sem)
-        lc = cross_entropy(cl, coarse_labels)
-        n_s, n_c = sl.shape[1], cl.shape[1]
-        loss = (ls * n_s + lc * n_c) / (n_s + n_c)
+
+    def step(sem, coarse):
+        """the trainer's step: wrapper forward with its key mask + forgetful causal mask, loss, backward, all-reduce"""
+        prep()
+        loss = wrapper(semantic_token_ids=sem, coarse_token_ids=coarse, return_loss=True)
         loss.backward()
-        bucket.finish()  # N > 1: the layers' slices were reduced under the backward; this sends the rest and scales
+        bucket.finish()  # N > 1: ONE all-reduce of the flat bucket (+ whatever the overlap hook has not sent) and 1/N
+        return loss
+
+    def step_direct():
+        """variant (a): bare CoarseTransformer.forward, pure causal attention (no key mask)"""
+        prep()
+        coarse_labels = torch.cat((coarse_d, eos), dim=1)
+        sl, cl = model(semantic_token_ids=sem_d, coarse_token_ids=coarse_d)
+        n_s, n_c = sl.shape[1], cl.shape[1]
+        loss = (cross_entropy(sl, sem_d) * n_s + cross_entropy(cl, coarse_labels) * n_c) / (n_s + n_c)
+        loss.backward()
+        bucket.finish()
         return loss
 
     def barrier():
@@ -270,31 +428,43 @@ def main_ours(args):
         return ms.item()
 
     for _ in range(max(args.warmup, 3)):
-        step(sem_d, coarse_d)
+        step(wsem_d, wco_d)
 
     # ---- device-resident timing ----
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     _lib.reset_launch_count()
-    ms_total = timed(lambda: step(sem_d, coarse_d), args.steps)
+    ms_total = timed(lambda: step(wsem_d, wco_d), args.steps)
     launches = _lib.launch_count() / args.steps
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host ids -> device, loss -> host, every step ----
     def e2e_step():
-        s = sem_pin.to(dev, non_blocking=True)
-        c = coarse_pin.to(dev, non_blocking=True)
+        s = wsem_pin.to(dev, non_blocking=True)
+        c = wco_pin.to(dev, non_blocking=True)
         return step(s, c).item()
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- variant (a): no key mask ----
+    for _ in range(2):
+        step_direct()
+    n_direct = max(3, args.steps // 2)
+    ms_direct = timed(step_direct, n_direct) / n_direct
+
+    # ---- collective alone (N > 1): the flat-bucket all-reduce timed on its own, max over ranks ----
+    ms_allreduce = None
+    if world > 1:
+        bucket.all_reduce_mean()
+        ms_allreduce = timed(lambda: bucket.all_reduce_mean(), 5) / 5
+
     # ---- roofline of the dominant kernel class (tcgen05 GEMM), events on the launching stream ----
     barrier()
     ops.profile_start()
     for _ in range(2):
-        step(sem_d, coarse_d)
+        step(wsem_d, wco_d)
     prof = ops.profile_stop()
 
     if rank != 0:
@@ -314,6 +484,8 @@ def main_ours(args):
             kern[cls].update(gbps=rate / 1e9, frac_of_hbm_peak=rate / 1e9 / pk["hbm"] if pk.get("hbm") else None)
         else:
             kern[cls]["tflops"] = rate / 1e12
+    traffic, traffic_src = gemm_traffic_from_profile()
+    step_tflop = 388e6 * BATCH * SEQ / 1e12  # 388 MFLOP/token fwd+bwd
 
     line = {
         "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -323,29 +495,46 @@ def main_ours(args):
                    "global_batch": world * BATCH, "seq_len": SEQ, "parallelism": f"dp{world}", "params": n_params,
                    "l2": "working set (~9 GB of saved activations per step) far exceeds the 126 MB L2"},
         "e2e": {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s",
-                "h2d_bytes_per_step": (sem_pin.numel() + coarse_pin.numel()) * 8, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": (wsem_pin.numel() + wco_pin.numel()) * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clocks,
+        "variants": {"direct_causal": {"tokens_per_s": tokens / (ms_direct * 1e-3), "ms_per_step": ms_direct,
+                                       "what": "CoarseTransformer.forward without key mask + the same two CE + bwd"}},
+        "step_mfu": {"algorithmic_tflop_per_step_per_gpu": step_tflop,
+                     "achieved_tflops": step_tflop / (ms_step * 1e-3), "peak": pk["tf_sustained"],
+                     "frac": step_tflop / (ms_step * 1e-3) / pk["tf_sustained"]},
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all fwd/dgrad/wgrad launches of a step)",
                      "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tf_sustained"] if pk["tf_sustained"] else None,
-                     # DRAM bytes (read + write) of the 108 GEMM launches of one step from an ncu capture of this
-                     # command (profiles/r01_ncu_gemm_dram_bytes_per_launch_one_step.csv): 13.60 GB + 3.52 GB
-                     "traffic": 17.12e9, "traffic_unit": "bytes per step over all launches of the class",
-                     "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
-                     "step_algorithmic_tflop": 388e6 * tokens / world / 1e12},
+                     "traffic": traffic, "traffic_unit": "DRAM bytes (read + write) per launch, class average",
+                     "traffic_source": traffic_src,
+                     "algorithmic_flops_per_launch": g_flops / g_n if g_n else None,
+                     "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)"},
         "kernels": kern,
     }
-    if world == 1:
-        try:
-            line["soundstream_encode"] = codec_encode_bench(dev)
-        except Exception as e:  # pragma: no cover
-            line["soundstream_encode"] = {"error": repr(e)}
+    if ms_allreduce is not None:
+        line["collective"] = {"what": f"all-reduce of the {n_params * 4 / 1e6:.0f} MB fp32 flat gradient bucket + 1/N",
+                              "ms_alone": ms_allreduce,
+                              "busbw_gbps": 2 * (world - 1) / world * n_params * 4 / (ms_allreduce * 1e-3) / 1e9}
+    if world == 1 and not args.headline_only:
+        del wrapper, model, bucket
+        torch.cuda.empty_cache()
+        cfgs = {}
+        for name, fn in (("C1_soundstream", codec_bench), ("C2_semantic_b8_n1024", config_c2),
+                         ("C4_fine_b16_n2049", config_c4), ("C5_decode_b1", config_c5)):
+            try:
+                cfgs[name] = fn(dev)
+            except Exception as e:  # pragma: no cover
+                cfgs[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+        line["configs"] = cfgs
+        line["soundstream_encode"] = cfgs["C1_soundstream"]
     if not args.no_cpu:
         try:
             tps, ms_cpu, cores = run_cpu(steps=1, warmup=1)
             line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port",
-                                    "sample": f"1 warm-up + 1 timed fwd+bwd of batch 1 x {SEQ} tokens, fp32 oracle port"}
+                                    "sample": f"1 warm-up + 1 timed fwd+bwd of batch 1 x {SEQ} tokens, fp32 oracle port "
+                                              "(restatement of the reference's modules; /root/reference is absent on the GPU box)"}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"error": repr(e)}
     emit(line)
@@ -360,6 +549,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline leg")
+    ap.add_argument("--headline-only", action="store_true", help="skip the extra C1/C2/C4/C5 legs of the N=1 line")
     a = ap.parse_args()
     # NCCL / torch may print banners ("NCCL version ...") on fd 1: keep stdout for the JSON line only
     sys.stdout.flush()

@@ -55,6 +55,25 @@ def check(name, a, b, tol=TOL):
         raise SystemExit(f"oracle does not reproduce the reference for {name}")
 
 
+
+def bf16_noise(m, loss_fn, grads):
+    """per-parameter RMS-relative deviation of the REFERENCE's own gradients when the same loss runs under bf16
+    autocast (the trainers wrap every step in accelerator.autocast(), trainer.py:577, 946, 1241, 1545).  Stored next to
+    the fp32 gradients so the GPU tests can bound the CUDA path (bf16 activations) by the reference's own bf16 noise on
+    these tiny, cancellation-heavy problems instead of by a hand-picked constant."""
+    m.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        loss = loss_fn()
+    loss.float().backward()
+    out = {}
+    for k, p in m.named_parameters():
+        if p.grad is not None and k in grads:
+            g = grads[k].float()
+            out[k] = ((p.grad.float() - g).pow(2).mean().sqrt() / g.pow(2).mean().sqrt().clamp(min=1e-20)).item()
+    m.zero_grad()
+    return out
+
+
 def golden_attend(ref):
     torch.manual_seed(11)
     b, h, n, d = 2, 4, 37, 64
@@ -116,11 +135,13 @@ def golden_semantic(ref):
     loss = w(semantic_token_ids=ids, return_loss=True)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    noise = bf16_noise(m, lambda: w(semantic_token_ids=ids, return_loss=True), grads)
     labels = torch.cat((ids, torch.full((2, 1), 50)), dim=1)
     ol, _ = ot.semantic_forward(st, labels[:, :-1], **hk)
     check("wrapper loss", ot.cross_entropy(ol, labels), loss.detach())
     torch.save(dict(kwargs=kw, state=st, ids=ids, mask=mask, logits=logits, logits_masked=logits_masked,
-                    cache12=cache, logits_inc=l_inc, loss=loss.detach(), grads=grads), GOLDEN / "semantic.pt")
+                    cache12=cache, logits_inc=l_inc, loss=loss.detach(), grads=grads, bf16_noise=noise),
+               GOLDEN / "semantic.pt")
 
 
 def golden_semantic_plain(ref):
@@ -143,8 +164,9 @@ def golden_semantic_plain(ref):
     loss = w(semantic_token_ids=ids, return_loss=True)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    noise = bf16_noise(m, lambda: w(semantic_token_ids=ids, return_loss=True), grads)
     torch.save(dict(kwargs=kw, state=st, ids=ids, mask=mask, logits=logits, logits_masked=logits_masked,
-                    loss=loss.detach(), grads=grads), GOLDEN / "semantic_plain.pt")
+                    loss=loss.detach(), grads=grads, bf16_noise=noise), GOLDEN / "semantic_plain.pt")
 
 
 def golden_coarse(ref):
@@ -187,6 +209,7 @@ def golden_coarse(ref):
     loss = w(semantic_token_ids=sem, coarse_token_ids=coarse_frames, return_loss=True)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    noise = bf16_noise(m, lambda: w(semantic_token_ids=sem, coarse_token_ids=coarse_frames, return_loss=True), grads)
     # oracle restatement of the wrapper arithmetic (audiolm_pytorch.py:1785-1854)
     sem_l = torch.cat((sem, torch.full((2, 1), 50)), 1)
     co_l = torch.cat((coarse_frames, torch.full((2, 1), 64)), 1)
@@ -195,7 +218,7 @@ def golden_coarse(ref):
     check("wrapper loss", ot.coarse_wrapper_loss(wsl, wcl, sem_l, co_l), loss.detach())
     torch.save(dict(kwargs=kw, state=st, sem=sem, coarse=coarse, mask=mask, sem_logits=sl, coarse_logits=cl,
                     sem_logits_masked=slm, coarse_logits_masked=clm, kv_a=kv_a, emb_a=emb_a, coarse_logits_b=cl_b,
-                    loss=loss.detach(), grads=grads), GOLDEN / "coarse.pt")
+                    loss=loss.detach(), grads=grads, bf16_noise=noise), GOLDEN / "coarse.pt")
 
 
 def golden_fine(ref):
@@ -256,6 +279,7 @@ def golden_relpos(ref):
     loss = ce(m(ids=ids), labels)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    noise = bf16_noise(m, lambda: ce(m(ids=ids).float(), labels), grads)
     st = clone_state(m)
     hk = dict(heads=2, depth=2)
     o, _ = ot.semantic_forward(st, ids, **hk)
@@ -267,7 +291,7 @@ def golden_relpos(ref):
     check("semantic cached step", oi, inc)
     check("semantic loss", ce(o, labels), loss.detach())
     out["semantic"] = dict(kwargs=kw, state=st, ids=ids, labels=labels, mask=mask, logits=lg, logits_masked=lgm,
-                           logits_inc=inc, loss=loss.detach(), grads=grads)
+                           logits_inc=inc, loss=loss.detach(), grads=grads, bf16_noise=noise)
 
     # ---- coarse ----
     torch.manual_seed(72)
@@ -291,6 +315,11 @@ def golden_relpos(ref):
     loss = ce(sl2, sem_labels) + ce(cl2, coarse_labels)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    def _loss():
+        a, b_ = m(semantic_token_ids=sem, coarse_token_ids=coarse)
+        return ce(a.float(), sem_labels) + ce(b_.float(), coarse_labels)
+    noise = bf16_noise(m, _loss, grads)
     st = clone_state(m)
     hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3)
     (osl, ocl), _ = ot.coarse_forward(st, sem, coarse, **hk)
@@ -303,7 +332,7 @@ def golden_relpos(ref):
     check("coarse loss", ce(osl, sem_labels) + ce(ocl, coarse_labels), loss.detach())
     out["coarse"] = dict(kwargs=kw, state=st, sem=sem, coarse=coarse, sem_labels=sem_labels,
                          coarse_labels=coarse_labels, sem_logits=sl, coarse_logits=cl, coarse_logits_b=cl_b,
-                         loss=loss.detach(), grads=grads)
+                         loss=loss.detach(), grads=grads, bf16_noise=noise)
 
     # ---- fine ----
     torch.manual_seed(73)
@@ -328,6 +357,11 @@ def golden_relpos(ref):
     loss = ce(cl2, c_labels) + ce(fl2, f_labels)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    def _loss():
+        a, b_ = m(coarse_token_ids=coarse, fine_token_ids=fine)
+        return ce(a.float(), c_labels) + ce(b_.float(), f_labels)
+    noise = bf16_noise(m, _loss, grads)
     st = clone_state(m)
     hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3, num_fine_quantizers=5)
     (ocl, ofl), _ = ot.fine_forward(st, coarse, fine, **hk)
@@ -339,8 +373,91 @@ def golden_relpos(ref):
     check("fine cached step", ofl_b, fl_b)
     check("fine loss", ce(ocl, c_labels) + ce(ofl, f_labels), loss.detach())
     out["fine"] = dict(kwargs=kw, state=st, coarse=coarse, fine=fine, c_labels=c_labels, f_labels=f_labels,
-                       coarse_logits=cl, fine_logits=fl, fine_logits_b=fl_b, loss=loss.detach(), grads=grads)
+                       coarse_logits=cl, fine_logits=fl, fine_logits_b=fl_b, loss=loss.detach(), grads=grads,
+                       bf16_noise=noise)
     torch.save(out, GOLDEN / "relpos.pt")
+
+
+fixed_fcm = ot.fixed_fcm
+
+
+def golden_wrappers(ref):
+    """training wrappers with the paths the plain goldens skip: FineTransformerWrapper.forward(return_loss=True)
+    (audiolm_pytorch.py:2041-2137), and Semantic / Coarse / Fine wrappers with the forgetful causal mask
+    (mask_prob=0.15) and unique_consecutive=True (:1513-1567, 1742-1854).  Loss + every parameter gradient."""
+    out = {}
+    print("wrappers (FCM mask, unique_consecutive, fine loss):")
+    ss = ref.ss.SoundStream(codebook_size=64, rq_num_quantizers=8, channels=4, use_local_attn=False, codebook_dim=32)
+    saved = ref.lm.generate_mask_with_prob
+    ref.lm.generate_mask_with_prob = fixed_fcm
+    try:
+        def grads_of(m):
+            return {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+        # ---- fine wrapper: plain (mask_prob=0) and with FCM ----
+        torch.manual_seed(81)
+        kw = dict(num_coarse_quantizers=3, num_fine_quantizers=5, codebook_size=64, dim=64, depth=2, heads=2,
+                  flash_attn=True)
+        m = ref.lm.FineTransformer(**kw).train()
+        perturb(m, 11)
+        coarse = torch.randint(0, 64, (2, 4, 3))
+        fine = torch.randint(0, 64, (2, 4, 5))
+        st = clone_state(m)
+        hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3, num_fine_quantizers=5)
+        res = {}
+        for tag, mp in (("plain", 0.0), ("fcm", 0.15)):
+            m.zero_grad()
+            w = ref.lm.FineTransformerWrapper(transformer=m, codec=ss, mask_prob=mp).train()
+            loss = w(coarse_token_ids=coarse, fine_token_ids=fine, return_loss=True)
+            loss.backward()
+            gr = grads_of(m)
+            res[tag] = dict(loss=loss.detach(), grads=gr, bf16_noise=bf16_noise(
+                m, lambda: w(coarse_token_ids=coarse, fine_token_ids=fine, return_loss=True), gr))
+            c2, f2 = coarse.reshape(2, -1), fine.reshape(2, -1)
+            mask = fixed_fcm((2, c2.shape[1] + f2.shape[1] - 1 + 2), mp) if mp > 0 else None
+            (ocl, ofl), _ = ot.fine_forward(st, c2, f2[:, :-1], self_attn_mask=mask, **hk)
+            n_c, n_f = ocl.shape[1], ofl.shape[1]
+            ol = (ot.cross_entropy(ocl, c2) * n_c + ot.cross_entropy(ofl, f2) * n_f) / (n_c + n_f)
+            check(f"fine wrapper loss ({tag})", ol, loss.detach())
+        out["fine"] = dict(kwargs=kw, state=st, coarse=coarse, fine=fine, **{f"{t}_{k}": v for t, r in res.items()
+                                                                                for k, v in r.items()})
+
+        # ---- semantic wrapper: unique_consecutive=True + FCM ----
+        torch.manual_seed(82)
+        kw = dict(num_semantic_tokens=50, dim=64, depth=2, heads=2, flash_attn=True)
+        m = ref.lm.SemanticTransformer(**kw).train()
+        perturb(m, 12)
+        ids = torch.randint(0, 50, (2, 24))
+        ids[0, 3:7] = ids[0, 3]           # runs of repeated ids -> ragged rows after unique_consecutive
+        ids[1, 10:12] = ids[1, 10]
+        ids[1, 15:20] = ids[1, 15]
+        w = ref.lm.SemanticTransformerWrapper(transformer=m, unique_consecutive=True, mask_prob=0.15).train()
+        loss = w(semantic_token_ids=ids, return_loss=True)
+        loss.backward()
+        gr = grads_of(m)
+        out["semantic"] = dict(kwargs=kw, state=clone_state(m), ids=ids, loss=loss.detach(), grads=gr,
+                               bf16_noise=bf16_noise(m, lambda: w(semantic_token_ids=ids, return_loss=True), gr))
+
+        # ---- coarse wrapper: unique_consecutive=True + FCM ----
+        torch.manual_seed(83)
+        kw = dict(num_semantic_tokens=50, codebook_size=64, num_coarse_quantizers=3, dim=64, depth=2, heads=2,
+                  flash_attn=True)
+        m = ref.lm.CoarseTransformer(**kw).train()
+        perturb(m, 13)
+        sem = torch.randint(0, 50, (2, 14))
+        sem[0, 2:6] = sem[0, 2]
+        sem[1, 8:10] = sem[1, 8]
+        coarse = torch.randint(0, 64, (2, 7, 3))
+        w = ref.lm.CoarseTransformerWrapper(transformer=m, codec=ss, unique_consecutive=True, mask_prob=0.15).train()
+        loss = w(semantic_token_ids=sem, coarse_token_ids=coarse, return_loss=True)
+        loss.backward()
+        gr = grads_of(m)
+        out["coarse"] = dict(kwargs=kw, state=clone_state(m), sem=sem, coarse=coarse, loss=loss.detach(), grads=gr,
+                             bf16_noise=bf16_noise(m, lambda: w(semantic_token_ids=sem, coarse_token_ids=coarse,
+                                                                return_loss=True), gr))
+    finally:
+        ref.lm.generate_mask_with_prob = saved
+    torch.save(out, GOLDEN / "wrappers.pt")
 
 
 def golden_sampling(ref):
@@ -411,18 +528,19 @@ def golden_soundstream(ref):
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     import random
-    random.seed(20240607)  # hyper-connections picks its initial stream with `random.randrange` (third_party.py:60)
     ref = ref_import.load()
+    fns = (golden_attend, golden_semantic, golden_semantic_plain, golden_coarse, golden_fine, golden_relpos,
+           golden_wrappers, golden_sampling, golden_soundstream)
+    only = set(sys.argv[1:])
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        golden_attend(ref)
-        golden_semantic(ref)
-        golden_semantic_plain(ref)
-        golden_coarse(ref)
-        golden_fine(ref)
-        golden_relpos(ref)
-        golden_sampling(ref)
-        golden_soundstream(ref)
+        for fn in fns:
+            if only and fn.__name__.replace("golden_", "") not in only:
+                continue
+            # hyper-connections picks its initial stream with `random.randrange` (third_party.py:60): seed per fixture
+            # so each file is reproducible on its own, whatever ran before it
+            random.seed(20240607 + sum(map(ord, fn.__name__)))
+            fn(ref)
     total = sum(p.stat().st_size for p in GOLDEN.glob("*.pt"))
     print(f"wrote {len(list(GOLDEN.glob('*.pt')))} fixtures, {total / 1e6:.2f} MB")
 

@@ -308,3 +308,9 @@ def fcm_mask(shape, mask_prob, generator=None):
     num = min(int(n * mask_prob), n - 1)
     idx = r.topk(num, dim=-1).indices
     return ~torch.zeros(shape).scatter(1, idx, 1.0).bool()
+
+def fixed_fcm(shape, mask_prob, device=None):
+    """deterministic stand-in for generate_mask_with_prob (audiolm_pytorch.py:82-89) used on BOTH sides of the wrapper
+    goldens: same construction (exactly int(n*p) keys dropped, position 0 kept), seeded by the shape."""
+    shape = tuple(shape)
+    return fcm_mask(shape, mask_prob, torch.Generator().manual_seed(1000 + shape[0] * 131 + shape[-1]))

@@ -104,3 +104,110 @@ def test_rvq_bit_exact_at_config_size():
     i2 = i.clone()
     i2[:, 5:] = -1
     assert err(ops.rvq_decode(i2, cb.to(DEV)), oc.rvq_decode(i2.cpu(), cb)) < 1e-5
+
+
+# ---- the kernels the C1 bench times, at C1 shapes --------------------------------------------
+C1_LAYERS = [(32, 48000), (64, 24000), (128, 6000), (256, 1200)]
+
+
+def _ru_weights(C, seed):
+    g = torch.Generator().manual_seed(seed)
+    w7 = torch.randn(C, C, 7, generator=g) * (0.7 / (7 * C) ** 0.5)
+    b7 = torch.randn(C, generator=g) * 0.1
+    w1 = torch.randn(C, C, 1, generator=g) * (0.7 / C ** 0.5)
+    b1 = torch.randn(C, generator=g) * 0.1
+    return w7, b7, w1, b1
+
+
+@pytest.mark.parametrize("C,T", C1_LAYERS)
+@pytest.mark.parametrize("d", [1, 3, 9])
+def test_residual_unit_product_path_vs_oracle(C, T, d):
+    """ResidualUnit.forward (the module path SoundStream.encoder takes: fused kernel at these widths) against the
+    oracle restatement of soundstream.py:362-369, and against the two-launch path built from ops.causal_conv1d."""
+    import torch.nn.functional as F
+
+    from audiolm_pytorch_b200 import ops
+    from audiolm_pytorch_b200 import soundstream as ss_mod
+    from oracle import codec as oc
+
+    w7, b7, w1, b1 = _ru_weights(C, 100 + C + d)
+    x = torch.randn(2, C, T, generator=torch.Generator().manual_seed(7 + d))
+    ref = x + F.elu(oc.causal_conv1d(F.elu(oc.causal_conv1d(x, w7, b7, dilation=d)), w1, b1))
+    ru = ss_mod.ResidualUnit(C, C, d)
+    with torch.no_grad():
+        getattr(ru.fn, "0").conv.weight.copy_(w7)
+        getattr(ru.fn, "0").conv.bias.copy_(b7)
+        getattr(ru.fn, "2").conv.weight.copy_(w1)
+        getattr(ru.fn, "2").conv.bias.copy_(b1)
+    ru = ru.to(DEV).eval()
+    xd = x.to(DEV)
+    with torch.no_grad():
+        y = ru(xd)
+        h = ops.causal_conv1d(xd, w7.to(DEV), b7.to(DEV), dilation=d, elu=True)
+        y2 = ops.causal_conv1d(h, w1.to(DEV), b1.to(DEV), elu=True, residual=xd)
+    scale = ref.abs().max().item()
+    assert err(y, ref) < 2e-4 * max(1.0, scale), (err(y, ref), scale)
+    assert err(y2, ref) < 2e-4 * max(1.0, scale)
+    assert err(y, y2) < 2e-4 * max(1.0, scale)
+    # first samples: the reflect halo (x[1..pad] mirrored) is the edge case of the in-kernel padding
+    assert err(y[..., :64], ref[..., :64]) < 2e-4 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,T", [(1, 32, 7, 1, 48000), (32, 64, 4, 2, 48000), (64, 128, 8, 4, 24000),
+                                            (128, 256, 10, 5, 6000), (256, 512, 16, 8, 1200), (512, 512, 3, 1, 150)])
+def test_encoder_convs_product_path_vs_oracle(cin, cout, k, s, T):
+    """the non-residual convs of the C1 encoder through CausalConv1d.forward (packed-weight tiled kernels)"""
+    from audiolm_pytorch_b200 import soundstream as ss_mod
+    from oracle import codec as oc
+
+    g = torch.Generator().manual_seed(cin + k)
+    conv = ss_mod.CausalConv1d(cin, cout, k, stride=s)
+    with torch.no_grad():
+        conv.conv.weight.copy_(torch.randn(cout, cin, k, generator=g) * (0.7 / (cin * k) ** 0.5))
+        conv.conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    x = torch.randn(2, cin, T, generator=g)
+    ref = oc.causal_conv1d(x, conv.conv.weight.detach(), conv.conv.bias.detach(), stride=s)
+    conv = conv.to(DEV).eval()
+    with torch.no_grad():
+        y = conv(x.to(DEV))
+    assert y.shape == ref.shape and err(y, ref) < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_c1_encoder_and_rvq_indices_vs_oracle():
+    """full C1 encoder (32 channels, strides 2/4/5/8, 48 000 samples -> 150 frames x 512) + 8-stage RVQ: encoder output
+    vs the oracle, code indices bit-exact on every frame whose best/second-best gap exceeds the encoder's own
+    fp32-accumulation-order noise; flip rate on the rest is printed."""
+    from audiolm_pytorch_b200.soundstream import SoundStream
+    from oracle import codec as oc
+    from oracle.transformer import sub
+
+    torch.manual_seed(12)
+    ss = SoundStream(codebook_size=1024, rq_num_quantizers=8, target_sample_hz=24000, use_local_attn=False)
+    g = torch.Generator().manual_seed(7)
+    for layer in ss.rq.rvqs[0].layers:
+        layer._codebook.embed.copy_(torch.randn(1, 1024, 512, generator=g) * 0.05)
+        layer._codebook.initted.fill_(True)
+    st = {k: v.detach().clone() for k, v in ss.state_dict().items()}
+    wave = torch.randn(2, 48000, generator=g)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    enc_ref = oc.encoder(sub(st, "encoder"), wave[:, None, :]).transpose(1, 2)          # b n c
+    cbs = oc.codebooks_of(st)
+    flat = enc_ref.reshape(-1, 512)
+    q_ref, i_ref = oc.rvq_encode(flat, cbs)
+    margin = oc.rvq_margin(flat, cbs)
+    ss = ss.to(DEV).eval()
+    with torch.no_grad():
+        enc = ss.encoder(wave.to(DEV)[:, None, :]).transpose(1, 2)
+        quant, idx, _ = ss(wave.to(DEV), return_encoded=True)
+    e = err(enc, enc_ref)
+    scale = enc_ref.abs().max().item()
+    print(f"C1 encoder max abs err {e:.3e} (scale {scale:.2f})")
+    assert e < 2e-4 * max(1.0, scale)
+    idx = idx.reshape(-1, 8).cpu()
+    safe = margin > max(20 * e, 1e-4)
+    print(f"margin-safe frames {safe.float().mean().item():.2%}, frames with any differing index "
+          f"{(idx != i_ref).any(-1).float().mean().item():.2%}")
+    assert safe.float().mean() > 0.5
+    assert torch.equal(idx[safe], i_ref[safe]), "RVQ indices must be bit-exact on margin-safe frames"
+    same = (idx == i_ref).all(-1)
+    assert err(quant.reshape(-1, 512)[same.to(DEV)], q_ref[same]) < 1e-4

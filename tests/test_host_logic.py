@@ -139,3 +139,41 @@ def test_flat_bucket_ranges():
         b.range_of([m[0].weight, m[1].weight])   # not adjacent in the bucket
     b.reduce_range_async(0, 15)                  # no process group: no-op
     b.finish()
+
+
+def test_batch_unique_consecutive_matches_per_row_loop():
+    """vectorised version vs the reference construction (audiolm_pytorch.py:162-164)"""
+    from torch import nn
+
+    from audiolm_pytorch_b200.audiolm import batch_unique_consecutive
+
+    def ref(t, pad_value):
+        rows = [torch.unique_consecutive(r) for r in t.unbind(0)]
+        return nn.utils.rnn.pad_sequence(rows, batch_first=True, padding_value=pad_value)
+
+    torch.manual_seed(0)
+    for shape, hi in [((4, 50), 3), ((3, 1), 5), ((2, 17), 100), ((5, 200), 2), ((1, 9), 1)]:
+        t = torch.randint(0, hi, shape)
+        assert torch.equal(batch_unique_consecutive(t, -1), ref(t, -1)), shape
+    t = torch.tensor([[1, 1, 2, -1, -1], [3, 4, 5, 6, 7]])
+    assert torch.equal(batch_unique_consecutive(t, -1), ref(t, -1))
+
+
+def test_flat_grad_bucket_survives_zero_grad_set_to_none():
+    """optimizer.zero_grad(set_to_none=True) detaches .grad from the bucket; sync_views() copies the fresh gradients in
+    and restores the aliasing before any collective / clip (parallel.py)."""
+    from audiolm_pytorch_b200.parallel import FlatGradBucket
+
+    m = torch.nn.Linear(4, 3)
+    b = FlatGradBucket(m.parameters())
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    opt.zero_grad()                      # set_to_none=True by default
+    assert m.weight.grad is None
+    m(torch.ones(2, 4)).sum().backward()
+    assert m.weight.grad.data_ptr() != b.flat.data_ptr()
+    n = b.grad_norm()                    # -> sync_views
+    assert m.weight.grad.data_ptr() == b.flat[:12].data_ptr()
+    assert torch.allclose(n, torch.cat([p.grad.flatten() for p in m.parameters()]).norm())
+    assert torch.equal(b.flat[:12].view(3, 4), torch.full((3, 4), 2.0))
+    b.zero_()
+    assert float(m.weight.grad.abs().sum()) == 0.0

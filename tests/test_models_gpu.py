@@ -26,8 +26,11 @@ def rms_rel(a, b):
     return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-12)).item()
 
 
-def check_grads(named, golden_grads):
-    """every parameter gradient vs the reference's.  Tensors: RMS-relative error < 6e-2.  The tiny hyper-connection
+def check_grads(named, golden_grads, noise=None):
+    """every parameter gradient vs the reference's fp32 gradient.  Tensors: RMS-relative error < max(7e-2, 2 x the
+    deviation the REFERENCE itself shows under bf16 autocast on the same problem) — `noise` is the golden's
+    `bf16_noise` dict (oracle/make_golden.py::bf16_noise); the CUDA path computes in bf16 like an autocast step, so
+    its distance to the fp32 gradients is bounded by the reference's own bf16 spread, not by fp32 round-off.  The tiny hyper-connection
     tensors (static_alpha/beta [4,5]/[4], the two scalars) are sums over every token of strongly cancelling
     bf16-noisy terms, so their error is measured against the largest gradient of the same kind across layers."""
     kind_scale = {}
@@ -42,7 +45,7 @@ def check_grads(named, golden_grads):
             err = (named[k].grad.float().cpu() - gr.float()).pow(2).mean().sqrt().item()
             errs[k] = (err / kind_scale[k.split(".")[-1]], 0.35)  # 40-68 tokens only; tighter check: *_more_tokens
         else:
-            errs[k] = (rms_rel(named[k].grad, gr), 7e-2)
+            errs[k] = (rms_rel(named[k].grad, gr), max(7e-2, 2.0 * (noise or {}).get(k, 0.0)))
     for k, (e, tol) in sorted(errs.items(), key=lambda kv: -kv[1][0] / kv[1][1])[:5]:
         print(f"  grad err {e:.4f} (tol {tol}) {k}")
     bad = {k: v for k, v in errs.items() if v[0] >= v[1]}
@@ -75,7 +78,7 @@ def test_semantic_forward_cache_loss_grads():
     loss = w(semantic_token_ids=ids, return_loss=True)
     assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
     loss.backward()
-    worst = check_grads(dict(m.named_parameters()), g["grads"])
+    worst = check_grads(dict(m.named_parameters()), g["grads"], g.get("bf16_noise"))
     print("semantic worst grad rms rel err", worst)
 
 
@@ -105,7 +108,7 @@ def test_coarse_forward_cache_loss_grads():
     loss = w(semantic_token_ids=sem, coarse_token_ids=coarse[:, :21], return_loss=True)
     assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
     loss.backward()
-    worst = check_grads(dict(m.named_parameters()), g["grads"])
+    worst = check_grads(dict(m.named_parameters()), g["grads"], g.get("bf16_noise"))
     print("coarse worst grad rms rel err", worst)
 
 
@@ -290,4 +293,4 @@ def test_single_residual_stream_path():
     loss = w(semantic_token_ids=ids, return_loss=True)
     assert abs(loss.item() - g["loss"].item()) < 2e-2 * abs(g["loss"].item())
     loss.backward()
-    check_grads(dict(m.named_parameters()), g["grads"])
+    check_grads(dict(m.named_parameters()), g["grads"], g.get("bf16_noise"))

@@ -179,3 +179,64 @@ def test_full_size_logits_vs_cpu_oracle(which):
         assert r.shape == g_.shape
         e = ((g_.float().cpu() - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()).item()
         assert e < 1e-2, (which, e)
+
+
+def test_c3_full_size_gradients_vs_oracle_autograd():
+    """C3 at full model size and sequence length (d1024 L6 h8, 2048 positions, batch 1) through the wrapper's own loss
+    WITH its key mask (CoarseTransformerWrapper.forward always passes one, audiolm_pytorch.py:1801-1812) and an FCM
+    mask: every parameter gradient of the hand-written backward vs torch autograd of the fp32 CPU oracle.
+    Tolerances as in test_models_gpu (bf16 activations vs fp32): 7 % RMS for tensors, 30 % of the largest same-kind
+    gradient for the <= 20-element hyper-connection tensors."""
+    from audiolm_pytorch_b200 import audiolm
+    from audiolm_pytorch_b200.heads import cross_entropy
+    from oracle import transformer as ot
+
+    torch.manual_seed(23)
+    m = audiolm.CoarseTransformer(**C3)
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "dynamic_alpha_fn" in n_ or "dynamic_beta_fn" in n_:
+                p.normal_(0, 0.02)
+            if "logit_weights" in n_:
+                p.mul_(0.05)
+    sem = torch.randint(0, 500, (1, 372))
+    coarse = torch.randint(0, 1024, (1, 1674))
+    sem_l = sem
+    co_l = torch.cat((coarse, torch.full((1, 1), 1024)), 1)
+    mask = ot.fcm_mask((1, 2048), 0.15, torch.Generator().manual_seed(3))
+    st = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    (osl, ocl), _ = ot.coarse_forward(st, sem, coarse, self_attn_mask=mask, heads=8, depth=6, codebook_size=1024,
+                                      num_coarse_quantizers=3)
+    oloss = ot.coarse_wrapper_loss(osl, ocl, sem_l, co_l)
+    oloss.backward()
+    m = m.to(DEV).train()
+    sl, cl = m(semantic_token_ids=sem.to(DEV), coarse_token_ids=coarse.to(DEV), self_attn_mask=mask.to(DEV))
+    n_s, n_c = sl.shape[1], cl.shape[1]
+    loss = (cross_entropy(sl, sem_l.to(DEV)) * n_s + cross_entropy(cl, co_l.to(DEV)) * n_c) / (n_s + n_c)
+    loss.backward()
+    assert abs(loss.item() - oloss.item()) < 1e-2 * abs(oloss.item())
+    shrunk = ("semantic_start_token", "coarse_start_token", "semantic_embedding.weight", "coarse_embedding.weight",
+              "coarse_quantize_embedding.weight")  # grad_shrink (audiolm_pytorch.py:93-94): x0.1 into the embeddings
+    golden = {}
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        g = st[k].grad
+        golden[k] = (g * 0.1 if k in shrunk else g)
+    kind_scale = {}
+    for k, gr in golden.items():
+        if gr.numel() <= 20:
+            kind = k.split(".")[-1]
+            kind_scale[kind] = max(kind_scale.get(kind, 0.0), gr.pow(2).mean().sqrt().item())
+    errs = {}
+    for k, gr in golden.items():
+        got = dict(m.named_parameters())[k].grad.float().cpu()
+        if gr.numel() <= 20:
+            errs[k] = ((got - gr).pow(2).mean().sqrt().item() / kind_scale[k.split(".")[-1]], 0.30)
+        else:
+            errs[k] = (((got - gr).pow(2).mean().sqrt() / gr.pow(2).mean().sqrt().clamp(min=1e-20)).item(), 7e-2)
+    for k, (e, tol) in sorted(errs.items(), key=lambda kv: -kv[1][0] / kv[1][1])[:8]:
+        print(f"  C3 full-size grad err {e:.4f} (tol {tol}) {k}")
+    bad = {k: v for k, v in errs.items() if v[0] >= v[1]}
+    assert not bad, bad

@@ -112,7 +112,7 @@ def _ce(lg, lb):
     return cross_entropy(lg, lb)
 
 
-def _check_grads(m, golden, tol=7e-2):
+def _check_grads(m, golden, tol=7e-2, noise=None):
     named = dict(m.named_parameters())
     kind_scale = {}
     for k, gr in golden.items():
@@ -130,7 +130,7 @@ def _check_grads(m, golden, tol=7e-2):
             e = (named[k].grad.float().cpu() - gr.float()).pow(2).mean().sqrt().item() / kind_scale[k.split(".")[-1]]
             t = 0.35
         else:
-            e, t = rms_rel(named[k].grad, gr), tol
+            e, t = rms_rel(named[k].grad, gr), max(tol, 2.0 * (noise or {}).get(k, 0.0))
         if e >= t:
             bad[k] = (e, t)
     assert not bad, bad
@@ -156,7 +156,7 @@ def test_semantic_rel_pos_bias_vs_reference_golden():
     loss = _ce(m(ids=ids), g["labels"].to(DEV))
     assert abs(loss.item() - g["loss"].item()) < 1e-2 * g["loss"].item()
     loss.backward()
-    _check_grads(m, g["grads"])
+    _check_grads(m, g["grads"], noise=g.get("bf16_noise"))
 
 
 def test_coarse_rel_pos_bias_vs_reference_golden():
@@ -197,7 +197,7 @@ def test_coarse_rel_pos_bias_vs_reference_golden():
     loss.backward()
     # these weights sit at a 1.06e-2 forward noise floor (control above; the flash golden's is 0.76e-2), and the
     # gradient noise scales with it: 7e-2 * 1.06 / 0.76 ~ 0.1 -> 0.13.  The d=256 oracle test below keeps 7e-2.
-    _check_grads(m, g["grads"], tol=0.13)
+    _check_grads(m, g["grads"], tol=0.13, noise=g.get("bf16_noise"))
 
 
 def test_fine_rel_pos_bias_vs_reference_golden():
@@ -222,7 +222,7 @@ def test_fine_rel_pos_bias_vs_reference_golden():
     loss = _ce(cl, g["c_labels"].to(DEV)) + _ce(fl, g["f_labels"].to(DEV))
     assert abs(loss.item() - g["loss"].item()) < 1e-2 * g["loss"].item()
     loss.backward()
-    _check_grads(m, g["grads"])
+    _check_grads(m, g["grads"], noise=g.get("bf16_noise"))
 
 
 def test_coarse_rel_pos_bias_larger_vs_oracle():

@@ -19,7 +19,7 @@ dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0)
 m = CoarseTransformer(num_semantic_tokens=50, codebook_size=64, num_coarse_quantizers=3, dim=256, depth=3, heads=4,
                       flash_attn=True).to(dev).train()
-bucket = FlatGradBucket(m.parameters())
+bucket = FlatGradBucket(m.parameters()).attach(m)
 torch.manual_seed(100 + rank)
 sem, coarse = torch.randint(0, 50, (4, 60), device=dev), torch.randint(0, 64, (4, 130), device=dev)
 

@@ -17,7 +17,7 @@ flash = "--no-flash" not in sys.argv
 dev = torch.device("cuda:0")
 torch.manual_seed(1234)
 model = CoarseTransformer(**{**bench.CFG, "flash_attn": flash}).to(dev).train()
-bucket = FlatGradBucket(model.parameters())
+bucket = FlatGradBucket(model.parameters()).attach(model)
 sem, coarse = (t.to(dev) for t in bench.synth_ids(bench.BATCH, 0))
 eos = torch.full((bench.BATCH, 1), bench.CFG["codebook_size"], device=dev)
 for _ in range(n):
