@@ -47,6 +47,9 @@ SIGNATURES: dict[str, list] = {
     "alm_residual_unit_fwd": [P, P, P, P, P, P, I, I, I, I, I, P],
     "alm_causal_conv1d_fwd": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "alm_causal_convT1d_fwd": [P, P, P, P, I, I, I, I, I, P],
+    "alm_codec_first_conv": [P, P, P, P, I, I, I, I, I, P],
+    "alm_codec_ru_tc": [P, P, P, P, P, I, I, I, I, I, I, P],
+    "alm_codec_conv_tc": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "alm_rvq_encode": [P, L, P, P, P, L, P, L, I, I, I, I, P],
     "alm_rvq_decode": [P, L, P, P, L, I, I, I, I, P],
 }

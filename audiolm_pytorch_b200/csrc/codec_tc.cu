@@ -1,0 +1,744 @@
+// SoundStream encoder on the tcgen05 tensor cores (sm_100a): split-bf16 ("bf16x3") implicit-GEMM causal convs.
+//
+// Reference arithmetic: soundstream.py:332-345 (CausalConv1d), :362-369 (ResidualUnit), :371-383 (EncoderBlock).
+//
+// Why tensor cores: the fp32 CUDA-core kernels (conv_tiled.cuh) are FMA-bound at 4 % of the HBM roofline the codec
+// is quoted against (18.4 GFLOP per 2-s clip vs 133.8 MB of algorithmic traffic).  fp32 operands are split as
+// x = x_hi + x_lo (two bf16, |x - x_hi - x_lo| <= 2^-17 |x|) and every product is evaluated as
+//   x_hi w_hi + x_lo w_hi + x_hi w_lo          (three kind::f16 MMAs, fp32 accumulation in TMEM)
+// which keeps the result within ~2^-16 relative of the fp32 product (the dropped x_lo w_lo term is 2^-18).
+//
+// Activation format between the encoder's layers ("C8S", channels-8 split): bf16 [B][2C/8][P][T/P][8]
+//   chunk c < C/8 holds the hi halves of channels 8c..8c+7, chunk C/8 + c their lo halves;
+//   P = 1 normally; a layer feeding a stride-s conv writes P = s phase planes (row t -> plane t % s, row t / s) so
+//   that every tap of the strided conv reads unit-stride rows.
+// Same bytes as fp32 [B][C][T].  One time step of one chunk is 16 B = one row of an UMMA no-swizzle core matrix:
+// a tile [chunk][row][8] is a K-major operand whose rows are 16 B apart (SBO = 128), so the start address of the
+// A descriptor can point at ANY row.  One staged tile [128 + 6d rows] therefore serves all 7 taps of a dilated conv
+// by shifting the descriptor start by j*d rows: no im2col, no per-tap reload.
+//
+// Kernels
+//   first_conv_kernel      fp32 wave [B][T] (C_in = 1) -> C8S, CUDA cores (7 FMAs per output, HBM-bound on the write)
+//   ru_tc_kernel<C>        fused ResidualUnit: y = x + ELU(W1 ELU(W7 *_d x + b7) + b1); the k=7 result goes
+//                          TMEM -> registers (bias, ELU, split) -> back into the SAME TMEM columns as the bf16 A operand
+//                          of the 1x1 conv (tcgen05.mma with A from tensor memory): it never touches shared memory
+//   conv_tc_kernel<..>     strided / plain causal conv as a pipelined implicit GEMM over (tap, k-step) units
+// Warp roles (all kernels): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (one accumulator row per thread).
+#include "alm_common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace alm {
+namespace ctc {
+
+__device__ uint4 g_zero_rows[64];  // 1 KB of zeros (static storage): source of constant-padding halo rows
+
+constexpr int TILE_M = 128;
+constexpr int MAX_HALO = 54;  // 6 * dilation 9
+constexpr int A_ROWS = TILE_M + MAX_HALO;
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v) - 1.f); }
+
+// 8 fp32 -> hi uint4, lo uint4 (bf16 pairs, channel e in the low half of word e/2 for even e)
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * i], h0, l0);
+    split_bf16(v[2 * i + 1], h1, l1);
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// element offset of (batch b, chunk c, time t) in a C8S tensor with `nch` chunks, P phase planes, T time steps
+__device__ __forceinline__ size_t c8s_off(int b, int c, int t, int nch, int P, int T) {
+  return ((((size_t)b * nch + c) * P + (t % P)) * (size_t)(T / P) + (t / P)) * 8;
+}
+
+// ---------------------------------------------------------------------------------------------
+// first conv: C_in = 1, kernel K <= 8, stride 1 -> C8S (P = 1)
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                         int B, int T, int K, int pad_mode) {
+  __shared__ float sw[COUT * 8];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < COUT * 8; i += blockDim.x) sw[i] = (i % 8) < K ? w[(i / 8) * K + (i % 8)] : 0.f;
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int pad = K - 1;
+  float xv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xv[j] = 0.f;
+    if (j < K) {
+      int u = t + j - pad;  // x index of tap j
+      if (u < 0) {
+        if (pad_mode == 0) u = -u;                 // reflect (edge sample excluded)
+        else if (pad_mode == 2) u = 0;             // replicate
+        else u = -1;                               // constant zero
+      }
+      if (u >= 0) xv[j] = __ldg(x + (size_t)b * T + u);
+    }
+  }
+  constexpr int NCH = COUT / 8;
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float acc = sb[c * 8 + e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(sw[(c * 8 + e) * 8 + j], xv[j], acc);  // taps >= K: w = 0 and x = 0
+      v[e] = acc;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(y + c8s_off(b, c, t, 2 * NCH, 1, T)) = hi;
+    *reinterpret_cast<uint4*>(y + c8s_off(b, NCH + c, t, 2 * NCH, 1, T)) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused ResidualUnit
+// ---------------------------------------------------------------------------------------------
+struct RuParams {
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+  const __nv_bfloat16* w;  // units (tap j = 0..6 of the k=7 conv, 7 = the 1x1 conv) x (k-step): [part][2][C][8]
+  const float* b7;
+  const float* b1;
+  int B, T, d, pad_mode, out_phases;
+  int tiles_per_clip, total_tiles;
+};
+
+template <int C>
+struct RuCfg {
+  static constexpr int NCHUNK = C / 8;
+  static constexpr int KSTEPS = C / 16;
+  static constexpr bool RESIDENT = C <= 64;       // all weights stay in shared memory for the CTA's lifetime
+  static constexpr int NBUF = C <= 128 ? 2 : 1;   // tiles in flight in tensor memory (each: D1 | D2 = 2C columns)
+  static constexpr int NA = C <= 128 ? 2 : 1;     // staged activation tiles
+  static constexpr int A_BYTES = 2 * NCHUNK * A_ROWS * 16;
+  static constexpr int UNIT_BYTES = 2 * 2 * C * 16;  // hi [2 chunks][C][16 B] + lo
+  static constexpr int NUNITS = 8 * KSTEPS;
+  static constexpr int NW = RESIDENT ? NUNITS : (C == 128 ? 4 : 2);
+  static constexpr int TMEM_COLS = NBUF * 2 * C;
+  static constexpr int SMEM_BYTES = NA * A_BYTES + NW * UNIT_BYTES + 2 * C * 4 + 512 + 128;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuParams p) {
+  using Cfg = RuCfg<C>;
+  constexpr int NCHUNK = Cfg::NCHUNK, KSTEPS = Cfg::KSTEPS, NA = Cfg::NA, NW = Cfg::NW, NBUF = Cfg::NBUF;
+  constexpr bool RESIDENT = Cfg::RESIDENT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + NA * Cfg::A_BYTES;
+  float* sBias = reinterpret_cast<float*>(sW + NW * Cfg::UNIT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * C);
+  uint64_t* a_full = bars;              // [2]
+  uint64_t* a_empty = bars + 2;         // [2]
+  uint64_t* d1_full = bars + 4;         // [2]
+  uint64_t* a2_full = bars + 6;         // [2]
+  uint64_t* d2_full = bars + 8;         // [2]
+  uint64_t* d2_empty = bars + 10;       // [2]
+  uint64_t* w_full = bars + 12;         // [<= 4] (resident: [0] only)
+  uint64_t* w_empty = bars + 16;        // [<= 4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&d1_full[i], 1);
+      mbar_init(&a2_full[i], 4);
+      mbar_init(&d2_full[i], 1);
+      mbar_init(&d2_empty[i], 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    sBias[i] = p.b7 ? p.b7[i] : 0.f;
+    sBias[C + i] = p.b1 ? p.b1[i] : 0.f;
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int halo = 6 * p.d;
+  auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+  auto has = [&](int i) { return i >= 0 && tile_of(i) < p.total_tiles; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== producer: bulk copies =====================
+      if (RESIDENT) {
+        mbar_arrive_expect_tx(&w_full[0], Cfg::NUNITS * Cfg::UNIT_BYTES);
+        for (int u = 0; u < Cfg::NUNITS; ++u)
+          bulk_copy_g2s(sW + u * Cfg::UNIT_BYTES, p.w + (size_t)u * (Cfg::UNIT_BYTES / 2), Cfg::UNIT_BYTES, &w_full[0]);
+      }
+      int wstage = 0;
+      uint32_t wphase = 0;
+      auto stream_units = [&](int u0, int u1) {
+        for (int u = u0; u < u1; ++u) {
+          mbar_wait(&w_empty[wstage], wphase ^ 1u);
+          mbar_arrive_expect_tx(&w_full[wstage], Cfg::UNIT_BYTES);
+          bulk_copy_g2s(sW + wstage * Cfg::UNIT_BYTES, p.w + (size_t)u * (Cfg::UNIT_BYTES / 2), Cfg::UNIT_BYTES,
+                        &w_full[wstage]);
+          if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
+        }
+      };
+      auto load_a = [&](int i) {
+        const int ab = i % NA;
+        mbar_wait(&a_empty[ab], (((uint32_t)(i / NA)) & 1u) ^ 1u);
+        const int tile = tile_of(i);
+        const int b = tile / p.tiles_per_clip;
+        const int t0 = (tile - b * p.tiles_per_clip) * TILE_M;
+        const int nmain = min(TILE_M, p.T - t0);
+        uint8_t* dst = sA + ab * Cfg::A_BYTES;
+        if (t0 >= halo) {
+          const uint32_t rows = halo + nmain;
+          mbar_arrive_expect_tx(&a_full[ab], 2 * NCHUNK * rows * 16);
+          for (int c = 0; c < 2 * NCHUNK; ++c)
+            bulk_copy_g2s(dst + c * (A_ROWS * 16), p.x + (((size_t)b * 2 * NCHUNK + c) * p.T + (t0 - halo)) * 8,
+                          rows * 16, &a_full[ab]);
+        } else {
+          // first tile(s) of a clip: rows with time < 0 come from the padding rule (soundstream.py:339-344)
+          const int nneg = halo - t0;          // halo rows with negative time
+          const uint32_t rows_pos = t0 + nmain;  // rows with time in [0, t0 + nmain)
+          uint32_t tx = 2 * NCHUNK * (rows_pos + nneg) * 16;
+          mbar_arrive_expect_tx(&a_full[ab], tx);
+          for (int c = 0; c < 2 * NCHUNK; ++c) {
+            const __nv_bfloat16* src = p.x + ((size_t)b * 2 * NCHUNK + c) * p.T * 8;
+            uint8_t* dc = dst + c * (A_ROWS * 16);
+            bulk_copy_g2s(dc + nneg * 16, src, rows_pos * 16, &a_full[ab]);
+            if (p.pad_mode == 0) {
+              for (int u = 1; u <= nneg; ++u)  // time -u  <-  x[u]  (reflect, edge sample excluded)
+                bulk_copy_g2s(dc + (nneg - u) * 16, src + (size_t)u * 8, 16, &a_full[ab]);
+            } else if (p.pad_mode == 2) {
+              for (int u = 1; u <= nneg; ++u) bulk_copy_g2s(dc + (nneg - u) * 16, src, 16, &a_full[ab]);
+            } else {
+              bulk_copy_g2s(dc, g_zero_rows, nneg * 16, &a_full[ab]);
+            }
+          }
+        }
+      };
+      if (has(0)) load_a(0);
+      for (int i = 0;; ++i) {
+        const bool h1 = has(i), h2 = has(i - (NBUF - 1));
+        if (!h1 && !h2) break;
+        if (NA == 2 && has(i + 1)) load_a(i + 1);
+        if (!RESIDENT && h1) stream_units(0, 7 * KSTEPS);
+        if (NA == 1 && has(i + 1)) load_a(i + 1);
+        if (!RESIDENT && h2) stream_units(7 * KSTEPS, 8 * KSTEPS);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, C, false, false);
+      if (RESIDENT) mbar_wait(&w_full[0], 0);
+      int wstage = 0;
+      uint32_t wphase = 0;
+      const uint32_t sw_addr = smem_u32(sW);
+      for (int i = 0;; ++i) {
+        const int i2 = i - (NBUF - 1);
+        const bool h1 = has(i), h2 = has(i2);
+        if (!h1 && !h2) break;
+        if (h1) {
+          const int ab = i % NA, tb = i % NBUF;
+          mbar_wait(&a_full[ab], ((uint32_t)(i / NA)) & 1u);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + ab * Cfg::A_BYTES);
+          const uint32_t d1 = tmem_base + tb * 2 * C;
+          for (int j = 0; j < 7; ++j) {
+            const uint32_t row_off = (uint32_t)(j * p.d) * 16u;
+#pragma unroll 1
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const int u = j * KSTEPS + kk;
+              uint32_t wb;
+              if (RESIDENT) {
+                wb = sw_addr + u * Cfg::UNIT_BYTES;
+              } else {
+                mbar_wait(&w_full[wstage], wphase);
+                tc_fence_after_sync();
+                wb = sw_addr + wstage * Cfg::UNIT_BYTES;
+              }
+              const uint64_t a_hi = umma_smem_desc_nosw(a_addr + (2 * kk) * (A_ROWS * 16) + row_off, 128, A_ROWS * 16);
+              const uint64_t a_lo =
+                  umma_smem_desc_nosw(a_addr + (NCHUNK + 2 * kk) * (A_ROWS * 16) + row_off, 128, A_ROWS * 16);
+              const uint64_t b_hi = umma_smem_desc_nosw(wb, 128, C * 16);
+              const uint64_t b_lo = umma_smem_desc_nosw(wb + 2 * C * 16, 128, C * 16);
+              umma_bf16_ss(d1, a_hi, b_hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16_ss(d1, a_lo, b_hi, idesc, 1u);
+              umma_bf16_ss(d1, a_hi, b_lo, idesc, 1u);
+              if (!RESIDENT) {
+                umma_commit(&w_empty[wstage]);
+                if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
+              }
+            }
+          }
+          umma_commit(&a_empty[ab]);  // the staged tile may be overwritten once these MMAs have read it
+          umma_commit(&d1_full[tb]);
+        }
+        if (h2) {
+          const int tb = i2 % NBUF;
+          const uint32_t ph = ((uint32_t)(i2 / NBUF)) & 1u;
+          mbar_wait(&a2_full[tb], ph);
+          mbar_wait(&d2_empty[tb], ph ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t d1 = tmem_base + tb * 2 * C;
+          const uint32_t d2 = d1 + C;
+#pragma unroll 1
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            const int u = 7 * KSTEPS + kk;
+            uint32_t wb;
+            if (RESIDENT) {
+              wb = sw_addr + u * Cfg::UNIT_BYTES;
+            } else {
+              mbar_wait(&w_full[wstage], wphase);
+              tc_fence_after_sync();
+              wb = sw_addr + wstage * Cfg::UNIT_BYTES;
+            }
+            const uint64_t b_hi = umma_smem_desc_nosw(wb, 128, C * 16);
+            const uint64_t b_lo = umma_smem_desc_nosw(wb + 2 * C * 16, 128, C * 16);
+            // A operand of k-step kk sits where E1 left it: hi pairs in columns [16 kk, 16 kk + 8), lo in the next 8
+            umma_bf16_ts(d2, d1 + 16 * kk, b_hi, idesc, kk > 0 ? 1u : 0u);
+            umma_bf16_ts(d2, d1 + 16 * kk + 8, b_hi, idesc, 1u);
+            umma_bf16_ts(d2, d1 + 16 * kk, b_lo, idesc, 1u);
+            if (!RESIDENT) {
+              umma_commit(&w_empty[wstage]);
+              if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
+            }
+          }
+          umma_commit(&d2_full[tb]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: one accumulator row per thread =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    for (int i = 0;; ++i) {
+      const int i2 = i - (NBUF - 1);
+      const bool h1 = has(i), h2 = has(i2);
+      if (!h1 && !h2) break;
+      if (h1) {
+        // ---- E1: D1 -> (+b7, ELU, split) -> the same columns as the packed bf16 A operand of the 1x1 conv ----
+        const int tb = i % NBUF;
+        mbar_wait(&d1_full[tb], ((uint32_t)(i / NBUF)) & 1u);
+        tc_fence_after_sync();
+        const uint32_t d1 = tmem_base + tb * 2 * C + lane_sel;
+#pragma unroll 1
+        for (int g = 0; g < C / 32; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(d1 + g * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ch = g * 32 + h * 16 + 2 * e;
+              const float v0 = elu1(__uint_as_float(r[h * 16 + 2 * e]) + sBias[ch]);
+              const float v1 = elu1(__uint_as_float(r[h * 16 + 2 * e + 1]) + sBias[ch + 1]);
+              __nv_bfloat16 h0, l0, h1_, l1;
+              split_bf16(v0, h0, l0);
+              split_bf16(v1, h1_, l1);
+              o[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1_) << 16);
+              o[8 + e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            tmem_st_32x32b_x16(d1 + g * 32 + h * 16, o);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a2_full[tb]);
+      }
+      if (h2) {
+        // ---- E2: D2 -> (+b1, ELU, + skip) -> split -> global (C8S) ----
+        const int tb = i2 % NBUF;
+        const int tile = tile_of(i2);
+        const int b = tile / p.tiles_per_clip;
+        const int t = (tile - b * p.tiles_per_clip) * TILE_M + row;
+        const bool valid = t < p.T;
+        mbar_wait(&d2_full[tb], ((uint32_t)(i2 / NBUF)) & 1u);
+        tc_fence_after_sync();
+        const uint32_t d2 = tmem_base + tb * 2 * C + C + lane_sel;
+#pragma unroll 1
+        for (int g = 0; g < C / 32; ++g) {
+          uint4 xh[4], xl[4];
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              xh[c] = __ldg(reinterpret_cast<const uint4*>(p.x + (((size_t)b * 2 * NCHUNK + g * 4 + c) * p.T + t) * 8));
+              xl[c] = __ldg(
+                  reinterpret_cast<const uint4*>(p.x + (((size_t)b * 2 * NCHUNK + NCHUNK + g * 4 + c) * p.T + t) * 8));
+            }
+          }
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(d2 + g * 32, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t hw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
+              const uint32_t lw[4] = {xl[c].x, xl[c].y, xl[c].z, xl[c].w};
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int ch = g * 32 + c * 8 + e;
+                const float xs = (e & 1) ? (bf16_hi(hw[e >> 1]) + bf16_hi(lw[e >> 1]))
+                                         : (bf16_lo(hw[e >> 1]) + bf16_lo(lw[e >> 1]));
+                v[e] = xs + elu1(__uint_as_float(r[c * 8 + e]) + sBias[C + ch]);
+              }
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              *reinterpret_cast<uint4*>(p.y + c8s_off(b, g * 4 + c, t, 2 * NCHUNK, p.out_phases, p.T)) = hi;
+              *reinterpret_cast<uint4*>(p.y + c8s_off(b, NCHUNK + g * 4 + c, t, 2 * NCHUNK, p.out_phases, p.T)) = lo;
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d2_empty[tb]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int C>
+static int launch_ru(const RuParams& p, cudaStream_t stream) {
+  using Cfg = RuCfg<C>;
+  auto kfn = ru_tc_kernel<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ALM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int ctas_per_sm = (Cfg::SMEM_BYTES <= 110 * 1024 && 2 * Cfg::TMEM_COLS <= 512) ? 2 : 1;
+  const int grid = min(p.total_tiles, num_sms() * ctas_per_sm);
+  kfn<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// plain / strided causal conv (dilation 1) as a pipelined implicit GEMM
+//   out[t, co] = b[co] + sum_{j < K} sum_ci W[co, ci, j] xp[ci, t*s + j],  xp[u] = x[u - (K - s)]  (soundstream.py:332-345)
+// Input: C8S with P = s phase planes, so tap j of output row t reads plane ((j - pad) mod s), row t + floor((j - pad) / s):
+// unit-stride rows for every tap.  One pipeline stage = one (tap, 16-channel k-step) unit: A hi/lo [2][128][16 B] each,
+// W hi/lo [2][BN][16 B] each; three MMAs per stage.
+// ---------------------------------------------------------------------------------------------
+struct ConvParams {
+  const __nv_bfloat16* x;   // C8S [B][2 Cin/8][s][Tin/s][8]
+  void* y;                  // C8S (out_phases) or fp32 [B][n_out][Cout]
+  const __nv_bfloat16* w;   // [ntile][tap][kstep][part][2][BN][8]
+  const float* bias;
+  int B, Cin, Cout, Tin, n_out, K, s, pad_mode, out_phases, out_fp32;
+  int m_tiles, n_tiles, total_tiles;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int A_BYTES = 4 * TILE_M * 16;       // hi c0, hi c1, lo c0, lo c1
+  static constexpr int W_BYTES = 4 * BN * 16;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int STAGES = BN == 256 ? 8 : 10;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + 128;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES; // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ksteps = p.Cin / 16;
+  const int nch = p.Cin / 8;            // chunks per part
+  const int units = p.K * ksteps;
+  const int pad = p.K - p.s;
+  const int rows_in = p.Tin / p.s;      // rows of one phase plane
+  // tile -> (b, mt, nt): n fastest so the two N halves of a wide layer run back to back on the same A rows (L2 reuse)
+  auto decode = [&](int tile, int& b, int& mt, int& nt) {
+    nt = tile % p.n_tiles;
+    const int r = tile / p.n_tiles;
+    mt = r % p.m_tiles;
+    b = r / p.m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int b, mt, nt;
+        decode(tile, b, mt, nt);
+        const int t0 = mt * TILE_M;
+        const int nrows = min(TILE_M, p.n_out - t0);
+        for (int j = 0; j < p.K; ++j) {
+          const int q = j - pad;
+          const int plane = ((q % p.s) + p.s) % p.s;
+          const int shift = (q - plane) / p.s;   // floor(q / s)
+          // rows of this tile whose source row is negative (left padding)
+          const int nneg = min(nrows, max(0, -(t0 + shift)));
+          for (int kk = 0; kk < ksteps; ++kk) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sw = sa + Cfg::A_BYTES;
+            mbar_arrive_expect_tx(&full[stage], 4 * nrows * 16 + Cfg::W_BYTES);
+            for (int part = 0; part < 2; ++part)
+              for (int cc = 0; cc < 2; ++cc) {
+                const int c = part * nch + 2 * kk + cc;
+                const __nv_bfloat16* plane0 = p.x + (((size_t)b * 2 * nch + c) * p.s) * (size_t)rows_in * 8;
+                uint8_t* dst = sa + (part * 2 + cc) * (TILE_M * 16);
+                if (nrows > nneg)
+                  bulk_copy_g2s(dst + nneg * 16, plane0 + ((size_t)plane * rows_in + (t0 + nneg + shift)) * 8,
+                                (nrows - nneg) * 16, &full[stage]);
+                for (int r = 0; r < nneg; ++r) {
+                  // x index u = (t0 + r) * s + q < 0: reflect -> x[-u]; replicate -> x[0]; constant -> 0
+                  const int u = (t0 + r) * p.s + q;
+                  const __nv_bfloat16* src;
+                  if (p.pad_mode == 0) src = plane0 + ((size_t)((-u) % p.s) * rows_in + (-u) / p.s) * 8;
+                  else if (p.pad_mode == 2) src = plane0;
+                  else src = reinterpret_cast<const __nv_bfloat16*>(g_zero_rows);
+                  bulk_copy_g2s(dst + r * 16, src, 16, &full[stage]);
+                }
+              }
+            bulk_copy_g2s(sw, p.w + (((size_t)nt * p.K + j) * ksteps + kk) * (size_t)(Cfg::W_BYTES / 2), Cfg::W_BYTES,
+                          &full[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        mbar_wait(&acc_empty[acc], (((uint32_t)(iter >> 1)) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int u = 0; u < units; ++u) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sw = sa + Cfg::A_BYTES;
+          const uint64_t a_hi = umma_smem_desc_nosw(sa, 128, TILE_M * 16);
+          const uint64_t a_lo = umma_smem_desc_nosw(sa + 2 * TILE_M * 16, 128, TILE_M * 16);
+          const uint64_t b_hi = umma_smem_desc_nosw(sw, 128, BN * 16);
+          const uint64_t b_lo = umma_smem_desc_nosw(sw + 2 * BN * 16, 128, BN * 16);
+          umma_bf16_ss(d, a_hi, b_hi, idesc, u > 0 ? 1u : 0u);
+          umma_bf16_ss(d, a_lo, b_hi, idesc, 1u);
+          umma_bf16_ss(d, a_hi, b_lo, idesc, 1u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+      int b, mt, nt;
+      decode(tile, b, mt, nt);
+      const int acc = iter & 1;
+      mbar_wait(&acc_full[acc], ((uint32_t)(iter >> 1)) & 1u);
+      tc_fence_after_sync();
+      const int t = mt * TILE_M + row;
+      const bool valid = t < p.n_out;
+      const int n0 = nt * BN;
+      const uint32_t d = tmem_base + acc * BN + lane_sel;
+      const int nch_out = p.Cout / 8;
+#pragma unroll 1
+      for (int g = 0; g < BN / 32; ++g) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32b_x32(d + g * 32, r);
+        tmem_ld_wait();
+        if (g == BN / 32 - 1) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+        const int ch0 = n0 + g * 32;
+        if (valid && ch0 < p.Cout) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + (p.bias ? __ldg(p.bias + ch0 + e) : 0.f);
+          if (p.out_fp32) {
+            float* dst = reinterpret_cast<float*>(p.y) + ((size_t)b * p.n_out + t) * p.Cout + ch0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          } else {
+            __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float v8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v8[e] = v[c * 8 + e];
+              uint4 hi, lo;
+              split8(v8, hi, lo);
+              const int chunk = ch0 / 8 + c;
+              *reinterpret_cast<uint4*>(yb + c8s_off(b, chunk, t, 2 * nch_out, p.out_phases, p.n_out)) = hi;
+              *reinterpret_cast<uint4*>(yb + c8s_off(b, nch_out + chunk, t, 2 * nch_out, p.out_phases, p.n_out)) = lo;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN>
+static int launch_conv(const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  auto kfn = conv_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ALM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = min(p.total_tiles, num_sms());
+  kfn<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+}  // namespace ctc
+}  // namespace alm
+
+extern "C" int alm_codec_first_conv(const float* x, const float* w, const float* bias, void* y, int B, int T, int Cout,
+                                    int K, int pad_mode, alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(x && w && y && B > 0 && T > 0, ALM_ERR_ARG);
+  ALM_REQUIRE(K >= 1 && K <= 8 && pad_mode >= 0 && pad_mode <= 2, ALM_ERR_UNSUPPORTED);
+  ALM_REQUIRE(T > K - 1, ALM_ERR_ARG);
+  dim3 grid(ceil_div(T, 128), B);
+  __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
+  if (Cout == 32) ctc::first_conv_kernel<32><<<grid, 128, 0, stream>>>(x, w, bias, yy, B, T, K, pad_mode);
+  else if (Cout == 64) ctc::first_conv_kernel<64><<<grid, 128, 0, stream>>>(x, w, bias, yy, B, T, K, pad_mode);
+  else return ALM_ERR_UNSUPPORTED;
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_codec_ru_tc(const void* x, void* y, const void* w_units, const float* b7, const float* b1, int B,
+                               int C, int T, int dilation, int pad_mode, int out_phases, alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(x && y && w_units && B > 0 && T > 0, ALM_ERR_ARG);
+  ALM_REQUIRE(dilation >= 1 && 6 * dilation <= ctc::MAX_HALO && pad_mode >= 0 && pad_mode <= 2, ALM_ERR_UNSUPPORTED);
+  ALM_REQUIRE(T > 6 * dilation, ALM_ERR_ARG);
+  ALM_REQUIRE(out_phases >= 1 && T % out_phases == 0, ALM_ERR_ARG);
+  ctc::RuParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w_units);
+  p.b7 = b7;
+  p.b1 = b1;
+  p.B = B; p.T = T; p.d = dilation; p.pad_mode = pad_mode; p.out_phases = out_phases;
+  p.tiles_per_clip = ceil_div(T, ctc::TILE_M);
+  p.total_tiles = p.tiles_per_clip * B;
+  switch (C) {
+    case 32: return ctc::launch_ru<32>(p, stream);
+    case 64: return ctc::launch_ru<64>(p, stream);
+    case 128: return ctc::launch_ru<128>(p, stream);
+    case 256: return ctc::launch_ru<256>(p, stream);
+    default: return ALM_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int alm_codec_conv_tc(const void* x, void* y, const void* w_units, const float* bias, int B, int Cin,
+                                 int Cout, int Tin, int K, int stride, int pad_mode, int out_phases, int out_fp32,
+                                 alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(x && y && w_units && B > 0 && Tin > 0, ALM_ERR_ARG);
+  ALM_REQUIRE(Cin % 16 == 0 && K >= stride && stride >= 1 && Tin % stride == 0, ALM_ERR_UNSUPPORTED);
+  ALM_REQUIRE(pad_mode >= 0 && pad_mode <= 2, ALM_ERR_UNSUPPORTED);
+  ALM_REQUIRE(Tin > K, ALM_ERR_ARG);
+  const int BN = Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64);
+  ALM_REQUIRE(Cout % BN == 0, ALM_ERR_UNSUPPORTED);
+  ctc::ConvParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.y = y;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(w_units);
+  p.bias = bias;
+  p.B = B; p.Cin = Cin; p.Cout = Cout; p.Tin = Tin; p.K = K; p.s = stride; p.pad_mode = pad_mode;
+  p.n_out = Tin / stride;  // causal padding K - s keeps exactly Tin / s outputs
+  p.out_phases = out_phases; p.out_fp32 = out_fp32;
+  ALM_REQUIRE(out_fp32 || (out_phases >= 1 && p.n_out % out_phases == 0), ALM_ERR_ARG);
+  p.m_tiles = ceil_div(p.n_out, ctc::TILE_M);
+  p.n_tiles = Cout / BN;
+  p.total_tiles = B * p.m_tiles * p.n_tiles;
+  if (BN == 256) return ctc::launch_conv<256>(p, stream);
+  if (BN == 128) return ctc::launch_conv<128>(p, stream);
+  return ctc::launch_conv<64>(p, stream);
+}

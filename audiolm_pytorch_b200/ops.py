@@ -461,6 +461,101 @@ def causal_conv_transpose1d(x, weight, bias=None, *, stride):
     return y
 
 
+# ---- SoundStream encoder on the tensor cores (csrc/codec_tc.cu) ---------------------------------------
+def c8s_pack(x, phases=1):
+    """fp32 [B, C, T] -> C8S bf16 [B, 2C/8, P, T/P, 8] (torch ops; boundaries and tests only)."""
+    B, C, T = x.shape
+    assert C % 8 == 0 and T % phases == 0
+    hi = x.to(bf16)
+    lo = (x - hi.float()).to(bf16)
+
+    def arr(t):
+        return t.reshape(B, C // 8, 8, T // phases, phases).permute(0, 1, 4, 3, 2)
+
+    return torch.cat((arr(hi), arr(lo)), dim=1).contiguous()
+
+
+def c8s_unpack(a):
+    """C8S bf16 [B, 2C/8, P, T/P, 8] -> fp32 [B, C, T]."""
+    B, nch2, P, Tp, _ = a.shape
+    nch = nch2 // 2
+    v = a[:, :nch].float() + a[:, nch:].float()
+    return v.permute(0, 1, 4, 3, 2).reshape(B, nch * 8, Tp * P)
+
+
+def _split_units(w, bn=None):
+    """w fp32 [Cout, Cin, K] -> bf16 [K, Cin/16, 2 (hi, lo), 2, Cout, 8] (optionally tiled over Cout by bn)."""
+    Cout, Cin, K = w.shape
+    assert Cin % 16 == 0
+    hi = w.to(bf16)
+    lo = (w - hi.float()).to(bf16)
+
+    def arr(t):
+        return t.permute(2, 1, 0).reshape(K, Cin // 16, 2, 8, Cout).permute(0, 1, 2, 4, 3)
+
+    st = torch.stack((arr(hi), arr(lo)), dim=2)                      # [K, kk, part, cc, Cout, 8]
+    if bn is not None:
+        st = st.reshape(K, Cin // 16, 2, 2, Cout // bn, bn, 8).permute(4, 0, 1, 2, 3, 5, 6)
+    return st.contiguous()
+
+
+def pack_ru_weights(w7, w1):
+    """ResidualUnit weights [C, C, 7], [C, C, 1] -> the unit layout alm_codec_ru_tc streams (tap 7 = the 1x1 conv)."""
+    return _split_units(torch.cat((w7.detach().float(), w1.detach().float()), dim=2))
+
+
+def conv_tc_bn(cout):
+    return 256 if cout >= 256 else (128 if cout >= 128 else 64)
+
+
+def pack_conv_weights(w):
+    return _split_units(w.detach().float(), bn=conv_tc_bn(w.shape[0]))
+
+
+def codec_first_conv(wave, weight, bias, *, pad_mode="reflect"):
+    """CausalConv1d(1, Cout, K) on fp32 [B, T] -> C8S [B, 2Cout/8, 1, T, 8] (soundstream.py:520)."""
+    _check_cuda(wave, weight, bias)
+    B, T = wave.shape
+    Cout, cin, K = weight.shape
+    assert cin == 1 and wave.dtype == f32
+    y = torch.empty(B, 2 * Cout // 8, 1, T, 8, device=wave.device, dtype=bf16)
+    with _timed("codec_first_conv", (B * T * 4 + B * Cout * T * 4), "byte"):
+        _lib.call("alm_codec_first_conv", wave.contiguous(), weight.detach().contiguous(),
+                  None if bias is None else bias.detach().contiguous(), y, B, T, Cout, K, PAD_MODES[pad_mode])
+    return y
+
+
+def codec_ru_tc(x, w_units, b7, b1, *, dilation, pad_mode="reflect", out_phases=1):
+    """fused ResidualUnit on C8S activations (P = 1 in, `out_phases` planes out)."""
+    _check_cuda(x, w_units, b7, b1)
+    B, nch2, P, T, _ = x.shape
+    C = nch2 * 4
+    assert P == 1 and x.dtype == bf16 and x.is_contiguous() and w_units.dtype == bf16 and w_units.is_contiguous()
+    assert w_units.numel() == 8 * (C // 16) * 2 * 2 * C * 8
+    y = torch.empty(B, nch2, out_phases, T // out_phases, 8, device=x.device, dtype=bf16)
+    with _timed("codec_ru_tc", 2.0 * B * C * T * 4, "byte"):
+        _lib.call("alm_codec_ru_tc", x, y, w_units, b7, b1, B, C, T, int(dilation), PAD_MODES[pad_mode],
+                  int(out_phases))
+    return y
+
+
+def codec_conv_tc(x, w_units, bias, *, cout, kernel_size, stride, pad_mode="reflect", out_phases=1, out_fp32=False):
+    """CausalConv1d(Cin, cout, kernel_size, stride) on C8S activations with P = stride planes."""
+    _check_cuda(x, w_units, bias)
+    B, nch2, P, Tp, _ = x.shape
+    Cin, Tin = nch2 * 4, P * Tp
+    assert P == stride and x.is_contiguous() and w_units.is_contiguous()
+    n_out = Tin // stride
+    if out_fp32:
+        y = torch.empty(B, n_out, cout, device=x.device, dtype=f32)
+    else:
+        y = torch.empty(B, 2 * cout // 8, out_phases, n_out // out_phases, 8, device=x.device, dtype=bf16)
+    with _timed("codec_conv_tc", 4.0 * B * (Cin * Tin + cout * n_out), "byte"):
+        _lib.call("alm_codec_conv_tc", x, y, w_units, bias, B, Cin, cout, Tin, int(kernel_size), int(stride),
+                  PAD_MODES[pad_mode], int(out_phases), int(out_fp32))
+    return y
+
+
 def rvq_encode(x, codebooks):
     """x [N, D] fp32, codebooks [Q, C, D] fp32 -> (quantized [N, D] fp32, indices [N, Q] int64)."""
     _check_cuda(x, codebooks)

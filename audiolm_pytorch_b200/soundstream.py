@@ -22,6 +22,7 @@ f32 = torch.float32
 
 
 FUSE_RESIDUAL_UNITS = True  # False: conv7 + conv1 as two launches (A/B tests)
+ENCODER_ON_TENSOR_CORES = True  # False: fp32 CUDA-core conv kernels for the whole encoder (A/B tests)
 
 
 def exists(v):
@@ -262,6 +263,72 @@ class SoundStream(nn.Module):
         m.load(path, strict=strict)
         return m.eval()
 
+    # ---- encoder on the tensor cores (csrc/codec_tc.cu) ------------------------------------------------
+    def _tc_plan(self):
+        """layer list for the split-bf16 tensor-core encoder, or None when this configuration is outside what those
+        kernels are built for (then the fp32 CUDA-core kernels run).  Structure follows soundstream.py:519-531."""
+        if not (ENCODER_ON_TENSOR_CORES and self.single_channel and self.encoder_attn is None):
+            return None
+        enc = list(self.encoder)
+        first, blocks, last = enc[0], enc[1:-1], enc[-1]
+        ok = (isinstance(first, CausalConv1d) and first.conv.kernel_size[0] <= 8 and first.conv.out_channels in (32, 64)
+              and first.stride == 1 and first.dilation == 1 and isinstance(last, CausalConv1d) and last.dilation == 1
+              and last.conv.in_channels % 16 == 0 and last.conv.out_channels % 64 == 0)
+        plan = []
+        for blk in blocks if ok else ():
+            *rus, down = list(blk)
+            for ru in rus:
+                c7, c1 = getattr(ru.fn, "0"), getattr(ru.fn, "2")
+                C = c7.conv.in_channels
+                ok = ok and (C in (32, 64, 128, 256) and c7.conv.out_channels == C and c7.conv.kernel_size[0] == 7
+                             and c1.conv.kernel_size[0] == 1 and 6 * c7.dilation <= 54 and c7.stride == 1)
+            ok = ok and down.dilation == 1 and down.conv.in_channels % 16 == 0 and down.conv.out_channels % 64 == 0
+            plan.append((rus, down))
+        return (first, plan, last) if ok else None
+
+    @staticmethod
+    def _cached(mod, name, params, build):
+        key = tuple((p_.data_ptr(), p_._version) for p_ in params)
+        hit = mod.__dict__.get(name)
+        if hit is None or hit[0] != key:
+            with torch.inference_mode(False), torch.no_grad():
+                hit = (key, build())
+            mod.__dict__[name] = hit
+        return hit[1]
+
+    def _encode_tc(self, wave, plan):
+        """wave fp32 [B, T] -> encoder output fp32 [B, n, codebook_dim] (channels-last, what the RVQ consumes).
+        Activations stay in the C8S split-bf16 layout between layers; every layer is one kernel launch."""
+        first, blocks, last = plan
+        h = ops.codec_first_conv(wave, first.conv.weight, first.conv.bias, pad_mode=first.pad_mode)
+        for rus, down in blocks:
+            for i, ru in enumerate(rus):
+                c7, c1 = getattr(ru.fn, "0"), getattr(ru.fn, "2")
+                wu = self._cached(ru, "_tc_units", [c7.conv.weight, c1.conv.weight],
+                                  lambda c7=c7, c1=c1: ops.pack_ru_weights(c7.conv.weight, c1.conv.weight))
+                h = ops.codec_ru_tc(h, wu, c7.conv.bias, c1.conv.bias, dilation=c7.dilation, pad_mode=c7.pad_mode,
+                                    out_phases=down.stride if i == len(rus) - 1 else 1)
+            if not rus:
+                raise NotImplementedError  # (guarded by _tc_plan: every block has residual units)
+            wu = self._cached(down, "_tc_units", [down.conv.weight], lambda d=down: ops.pack_conv_weights(d.conv.weight))
+            h = ops.codec_conv_tc(h, wu, down.conv.bias, cout=down.conv.out_channels,
+                                  kernel_size=down.conv.kernel_size[0], stride=down.stride, pad_mode=down.pad_mode)
+        wu = self._cached(last, "_tc_units", [last.conv.weight], lambda: ops.pack_conv_weights(last.conv.weight))
+        return ops.codec_conv_tc(h, wu, last.conv.bias, cout=last.conv.out_channels,
+                                 kernel_size=last.conv.kernel_size[0], stride=1, pad_mode=last.pad_mode, out_fp32=True)
+
+    def encode_frames(self, x):
+        """x [B, 1, T] fp32 -> encoder output [B, n, codebook_dim] channels-last (soundstream.py:827-836)."""
+        plan = self._tc_plan()
+        T = x.shape[-1]
+        frames = T // self.seq_len_multiple_of
+        # every residual unit needs more samples than its reflect halo (6 x dilation <= 54); the shortest ones see
+        # frames x last stride samples
+        if plan is not None and x.is_cuda and T % self.seq_len_multiple_of == 0 and frames >= 4 \
+                and frames * self.strides[-1] > 54:
+            return self._encode_tc(x[:, 0].to(f32).contiguous(), plan)
+        return self.encoder(x.to(f32)).transpose(1, 2).contiguous()
+
     # ---- hot path ----------------------------------------------------------------------------------
     def process_input(self, x, input_sample_hz=None, curtail_from_left=False):
         lead = x.shape[:-1]
@@ -297,7 +364,7 @@ class SoundStream(nn.Module):
         if exists(is_denoising) or exists(target):
             raise NotImplementedError("FiLM denoising / target losses are outside this build")
         x, lead = self.process_input(x, input_sample_hz=input_sample_hz, curtail_from_left=curtail_from_left)
-        h = self.encoder(x.to(f32)).transpose(1, 2).contiguous()      # b n c
+        h = self.encode_frames(x)                                      # b n c
         quantized, indices, commit_loss = self.rq(h)
         if return_codes_only:
             return indices

@@ -232,6 +232,29 @@ int alm_causal_conv1d_fwd(const float* x, const float* w, const float* bias, con
 int alm_residual_unit_fwd(const float* x, const float* w7_packed, const float* b7, const float* w1_packed,
                           const float* b1, float* y, int B, int C, int T, int dilation, int pad_mode,
                           alm_stream_t stream);
+/*
+ * SoundStream encoder on the tensor cores (csrc/codec_tc.cu): split-bf16 ("bf16x3": x_hi w_hi + x_lo w_hi + x_hi w_lo,
+ * fp32 accumulation) implicit-GEMM causal convs.  Activations travel between these three calls in the "C8S" layout
+ *   bf16 [B][2C/8][P][T/P][8]   (chunk c < C/8: hi halves of channels 8c..8c+7, chunk C/8 + c: their lo halves;
+ *                                P phase planes: time t lives in plane t % P, row t / P; same bytes as fp32 [B][C][T]).
+ * Replaces the same reference calls as alm_causal_conv1d_fwd / alm_residual_unit_fwd (soundstream.py:332-383) when the
+ * whole encoder runs in this format; results agree with the fp32 path to ~1e-5 relative.
+ *
+ * alm_codec_first_conv: CausalConv1d(1, Cout, K <= 8) on fp32 wave [B][T] -> C8S (P = 1).  Cout in {32, 64}.
+ * alm_codec_ru_tc:      fused ResidualUnit  y = x + ELU(W1 ELU(W7 *_dil x + b7) + b1), C in {32, 64, 128, 256},
+ *                       dilation <= 9; x in C8S (P = 1), y in C8S with out_phases planes.  w_units: bf16
+ *                       [8 taps (7 = the 1x1 conv)][C/16 k-steps][hi, lo][2][C][8] (ops.pack_ru_weights).
+ * alm_codec_conv_tc:    CausalConv1d(Cin, Cout, K, stride) with dilation 1; x in C8S with P = stride planes; y in C8S
+ *                       (out_phases) or, out_fp32 = 1, fp32 channels-last [B][Tin/stride][Cout] (the RVQ input).
+ *                       w_units: bf16 [Cout/BN][K][Cin/16][hi, lo][2][BN][8], BN = min(256, largest of 64/128/256 <= Cout).
+ * pad_mode: 0 reflect, 1 constant zero, 2 replicate.
+ */
+int alm_codec_first_conv(const float* x, const float* w, const float* bias, void* y, int B, int T, int Cout, int K,
+                         int pad_mode, alm_stream_t stream);
+int alm_codec_ru_tc(const void* x, void* y, const void* w_units, const float* b7, const float* b1, int B, int C, int T,
+                    int dilation, int pad_mode, int out_phases, alm_stream_t stream);
+int alm_codec_conv_tc(const void* x, void* y, const void* w_units, const float* bias, int B, int Cin, int Cout, int Tin,
+                      int K, int stride, int pad_mode, int out_phases, int out_fp32, alm_stream_t stream);
 int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
                            int n, int stride, alm_stream_t stream);
 /*

@@ -211,3 +211,63 @@ def test_c1_encoder_and_rvq_indices_vs_oracle():
     assert torch.equal(idx[safe], i_ref[safe]), "RVQ indices must be bit-exact on margin-safe frames"
     same = (idx == i_ref).all(-1)
     assert err(quant.reshape(-1, 512)[same.to(DEV)], q_ref[same]) < 1e-4
+
+
+# ---- tensor-core encoder kernels (csrc/codec_tc.cu): split-bf16 implicit GEMM in the C8S layout --------------------
+def test_codec_first_conv_tc():
+    from audiolm_pytorch_b200 import ops
+    from oracle import codec as oc
+
+    g = torch.Generator().manual_seed(3)
+    w, b = torch.randn(32, 1, 7, generator=g) * 0.3, torch.randn(32, generator=g) * 0.1
+    x = torch.randn(3, 1, 5000, generator=g)
+    for mode in ("reflect", "constant"):
+        ref = oc.causal_conv1d(x, w, b, pad_mode=mode)
+        y = ops.c8s_unpack(ops.codec_first_conv(x[:, 0].to(DEV), w.to(DEV), b.to(DEV), pad_mode=mode))
+        assert err(y, ref) < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("C,T", [(32, 5000), (64, 3000), (128, 1500), (256, 700)])
+@pytest.mark.parametrize("d,phases,mode", [(1, 1, "reflect"), (3, 1, "constant"), (9, 4, "reflect"), (9, 5, "reflect")])
+def test_residual_unit_tc_vs_oracle(C, T, d, phases, mode):
+    """alm_codec_ru_tc (tcgen05, A operand of the 1x1 conv in tensor memory) vs soundstream.py:362-369 restated; ragged
+    last tile (T % 128 != 0), reflect / constant halo, phase-split output as fed to the strided convs."""
+    import torch.nn.functional as F
+
+    from audiolm_pytorch_b200 import ops
+    from oracle import codec as oc
+
+    w7, b7, w1, b1 = _ru_weights(C, 200 + C + d)
+    x = torch.randn(2, C, T, generator=torch.Generator().manual_seed(17 + d))
+    ref = x + F.elu(oc.causal_conv1d(F.elu(oc.causal_conv1d(x, w7, b7, dilation=d, pad_mode=mode)), w1, b1))
+    xc = ops.c8s_pack(x.to(DEV))
+    wu = ops.pack_ru_weights(w7.to(DEV), w1.to(DEV))
+    y = ops.codec_ru_tc(xc, wu, b7.to(DEV), b1.to(DEV), dilation=d, pad_mode=mode, out_phases=phases)
+    assert y.shape == (2, 2 * C // 8, phases, T // phases, 8)
+    got = ops.c8s_unpack(y)
+    scale = max(1.0, ref.abs().max().item())
+    e = err(got, ref)
+    print(f"RU tc C={C} d={d}: max abs err {e:.2e} (scale {scale:.2f})")
+    assert e < 1e-4 * scale
+    assert err(got[..., :64], ref[..., :64]) < 1e-4 * scale
+
+
+@pytest.mark.parametrize("cin,cout,k,s,T", [(32, 64, 4, 2, 4000), (64, 128, 8, 4, 2000), (128, 256, 10, 5, 1500),
+                                            (256, 512, 16, 8, 1200), (512, 512, 3, 1, 150)])
+@pytest.mark.parametrize("mode", ["reflect", "constant"])
+def test_conv_tc_vs_oracle(cin, cout, k, s, T, mode):
+    from audiolm_pytorch_b200 import ops
+    from oracle import codec as oc
+
+    g = torch.Generator().manual_seed(cin + k)
+    w = torch.randn(cout, cin, k, generator=g) * (0.7 / (cin * k) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(2, cin, T, generator=g)
+    ref = oc.causal_conv1d(x, w, b, stride=s, pad_mode=mode)
+    xc = ops.c8s_pack(x.to(DEV), phases=s)
+    wu = ops.pack_conv_weights(w.to(DEV))
+    y = ops.codec_conv_tc(xc, wu, b.to(DEV), cout=cout, kernel_size=k, stride=s, pad_mode=mode)
+    scale = max(1.0, ref.abs().max().item())
+    assert err(ops.c8s_unpack(y), ref) < 1e-4 * scale
+    y32 = ops.codec_conv_tc(xc, wu, b.to(DEV), cout=cout, kernel_size=k, stride=s, pad_mode=mode, out_fp32=True)
+    assert err(y32.transpose(1, 2), ref) < 1e-4 * scale
