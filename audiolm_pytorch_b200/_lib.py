@@ -51,6 +51,9 @@ SIGNATURES: dict[str, list] = {
     "alm_codec_ru_tc": [P, P, P, P, P, I, I, I, I, I, I, P],
     "alm_codec_conv_tc": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
     "alm_rvq_encode": [P, L, P, P, P, L, P, L, I, I, I, I, P],
+    "alm_rvq_pack_codebooks": [P, P, P, L, I, P],
+    "alm_rvq_prepare": [P, L, P, P, L, P, I, I, P],
+    "alm_rvq_select": [P, L, P, P, P, P, L, P, P, L, I, I, I, I, P],
     "alm_rvq_decode": [P, L, P, P, L, I, I, I, I, P],
 }
 

@@ -572,6 +572,41 @@ def rvq_encode(x, codebooks):
     return quant, idx
 
 
+def rvq_pack_codebooks(codebooks):
+    """codebooks fp32 [Q, C, D] -> (packed bf16 [Q, C, 3D] = [hi | hi | lo], e2 fp32 [Q, C]) for rvq_encode_tc."""
+    _check_cuda(codebooks)
+    Q, C, D = codebooks.shape
+    cb = codebooks.to(f32).contiguous()
+    packed = torch.empty(Q, C, 3 * D, device=cb.device, dtype=bf16)
+    e2 = torch.empty(Q, C, device=cb.device, dtype=f32)
+    _lib.call("alm_rvq_pack_codebooks", cb, packed, e2, Q * C, D)
+    return cb, packed, e2
+
+
+def rvq_encode_tc(x, packed_codebooks):
+    """x [N, D] fp32 -> (quantized [N, D] fp32, indices [N, Q] int64); distance GEMMs on the tensor cores, the
+    winner of every stage chosen by exact fp32 re-evaluation of the candidates (csrc/rvq_tc.cu)."""
+    cb, packed, e2 = packed_codebooks
+    _check_cuda(x, cb)
+    assert x.dtype == f32 and x.stride(-1) == 1
+    N, D = x.shape
+    Q, C, _ = cb.shape
+    assert D % 8 == 0
+    dev = x.device
+    r = torch.empty(N, D, device=dev, dtype=f32)
+    quant = torch.empty(N, D, device=dev, dtype=f32)
+    rp = torch.empty(N, 3 * D, device=dev, dtype=bf16)
+    scores = torch.empty(N, C, device=dev, dtype=f32)
+    idx = torch.empty(N, Q, device=dev, dtype=torch.int64)
+    with _timed("rvq_encode_tc", 2.0 * N * Q * C * D):
+        _lib.call("alm_rvq_prepare", x, x.stride(0), r, quant, D, rp, N, D)
+        for q in range(Q):
+            gemm(rp, packed[q], out=scores, cls="rvq_score_gemm")
+            _lib.call("alm_rvq_select", scores, C, e2[q], cb[q], r, quant, D, rp, idx[:, q:], Q, N, D, C,
+                      int(q + 1 < Q))
+    return quant, idx
+
+
 def rvq_decode(indices, codebooks):
     """indices [N, Q] int64 (-1 = dropped) -> sum of selected codes [N, D] fp32."""
     _check_cuda(indices, codebooks)

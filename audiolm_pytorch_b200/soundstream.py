@@ -22,6 +22,7 @@ f32 = torch.float32
 
 
 FUSE_RESIDUAL_UNITS = True  # False: conv7 + conv1 as two launches (A/B tests)
+RVQ_ON_TENSOR_CORES = True      # False: fp32 CUDA-core search kernel (A/B tests)
 ENCODER_ON_TENSOR_CORES = True  # False: fp32 CUDA-core conv kernels for the whole encoder (A/B tests)
 
 
@@ -143,7 +144,17 @@ class ResidualVQ(nn.Module):
         if not all(bool(l._codebook.initted.item()) for l in self.layers):
             raise RuntimeError("codebooks are not initialised (load a checkpoint; k-means init is not built)")
         b, n, d = x.shape
-        quant, idx = ops.rvq_encode(x.reshape(b * n, d).to(f32).contiguous(), self.codebooks())
+        flat = x.reshape(b * n, d).to(f32).contiguous()
+        if RVQ_ON_TENSOR_CORES and d % 8 == 0:
+            embeds = [l._codebook.embed for l in self.layers]
+            key = tuple((e.data_ptr(), e._version) for e in embeds)
+            if self.__dict__.get("_tc_key") != key:
+                with torch.inference_mode(False), torch.no_grad():
+                    self.__dict__["_tc_pack"] = ops.rvq_pack_codebooks(self.codebooks())
+                self.__dict__["_tc_key"] = key
+            quant, idx = ops.rvq_encode_tc(flat, self.__dict__["_tc_pack"])
+        else:
+            quant, idx = ops.rvq_encode(flat, self.codebooks())
         return quant.view(b, n, d), idx.view(b, n, -1), torch.zeros(1, len(self.layers), device=x.device)
 
     def get_output_from_indices(self, indices):

@@ -265,6 +265,23 @@ int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, fl
  */
 int alm_rvq_encode(const float* x, int64_t ldx, const float* codebooks, float* e2_workspace, float* quantized,
                    int64_t ldq, int64_t* indices, int64_t ldi, int N, int D, int C, int Q, alm_stream_t stream);
+/*
+ * Residual VQ search with the distance GEMM on the tensor cores (csrc/rvq_tc.cu); same reference call as
+ * alm_rvq_encode (soundstream.py:840).  Per stage q the host runs
+ *     alm_gemm_bf16(R' [N, 3D], B'_q [C, 3D]) -> scores [N, C] fp32      (R' = [r_hi | r_lo | r_hi], B' = [e_hi | e_hi | e_lo])
+ *     alm_rvq_select(scores, e2_q, codebook_q, r, quantized, R', indices + q, ...)
+ * select re-evaluates every candidate within the bf16x3 error bound of the best approximate score with the exact fp32
+ * expansion sqrt(max(|r|^2 + |e|^2 - 2 r.e, 0)) (lowest index on ties), then r -= e, quantized += e, R' <- split(r).
+ * alm_rvq_pack_codebooks: codebooks fp32 [rows = Q*C, D] -> packed bf16 [rows, 3D] + e2 [rows] (once per weight version).
+ * alm_rvq_prepare: r = x, quantized = 0, R' = split(x).
+ */
+int alm_rvq_pack_codebooks(const float* codebooks, void* packed, float* e2, int64_t rows, int D, alm_stream_t stream);
+int alm_rvq_prepare(const float* x, int64_t ldx, float* r, float* quantized, int64_t ldq, void* rp, int N, int D,
+                    alm_stream_t stream);
+int alm_rvq_select(const float* scores, int64_t lds, const float* e2, const float* codebook, float* r, float* quantized,
+                   int64_t ldq, void* rp, int64_t* indices, int64_t ldi, int N, int D, int C, int write_rp,
+                   alm_stream_t stream);
+
 /* get_output_from_indices (soundstream.py:697): out[n,:] = sum_q codebooks[q][indices[n,q]] (-1 -> skip) */
 int alm_rvq_decode(const int64_t* indices, int64_t ldi, const float* codebooks, float* out, int64_t ldo, int N, int D,
                    int C, int Q, alm_stream_t stream);

@@ -79,7 +79,8 @@ def test_soundstream_golden_end_to_end():
     assert err(recon_idx, recon) < 1e-5  # README.md:100-113 round trip
 
 
-def test_rvq_bit_exact_at_config_size():
+@pytest.mark.parametrize("impl", ["fp32_cuda_cores", "tensor_cores"])
+def test_rvq_bit_exact_at_config_size(impl):
     """C1 sizes: 8 stages x 1024 codes x 512 dims.  Rows whose best/second-best gap exceeds fp32 noise must
     match the oracle exactly; the flip rate on the rest is reported."""
     from audiolm_pytorch_b200 import ops
@@ -90,7 +91,10 @@ def test_rvq_bit_exact_at_config_size():
     x = torch.randn(600, 512) * 3
     q_ref, i_ref = oc.rvq_encode(x, cb)
     margin = oc.rvq_margin(x, cb)
-    q, i = ops.rvq_encode(x.to(DEV), cb.to(DEV))
+    if impl == "tensor_cores":   # distance GEMM on tcgen05 + exact fp32 re-rank of the candidates (csrc/rvq_tc.cu)
+        q, i = ops.rvq_encode_tc(x.to(DEV), ops.rvq_pack_codebooks(cb.to(DEV)))
+    else:
+        q, i = ops.rvq_encode(x.to(DEV), cb.to(DEV))
     safe = margin > 1e-3
     assert safe.float().mean() > 0.9
     assert torch.equal(i.cpu()[safe], i_ref[safe])
