@@ -24,7 +24,9 @@
 //                          of the 1x1 conv (tcgen05.mma with A from tensor memory): it never touches shared memory
 //   conv_tc_kernel<..>     strided / plain causal conv as a pipelined implicit GEMM over (tap, k-step) units
 // Warp roles (all kernels): warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (one accumulator row per thread).
+// warps 4-11 = epilogue (one accumulator row per thread, two warps per TMEM lane quadrant splitting the columns).
+// Activation tiles are staged with 16-B cp.async by the whole producer warp (1-D bulk copies of ~2 KB measured
+// ~8 B/clk/SM: profiles/r02_codec_layers_a.txt), weights with large bulk copies.
 #include "alm_common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -108,6 +110,36 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// shared pieces
+// ---------------------------------------------------------------------------------------------
+constexpr int NEW = 8;                       // epilogue warps (two per TMEM lane quadrant)
+constexpr int NSUB = NEW / 4;
+constexpr int CTA_THREADS = 32 * (4 + NEW);  // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4.. epilogue
+
+// row `t` of a C8S tensor with P phase planes: element offset of chunk 0 (add c * chunk_stride for chunk c)
+struct RowAddr {
+  size_t off;           // ((b * nch) * P + t % P) * (T / P) + t / P, in 8-element rows, times 8
+  size_t chunk_stride;  // elements between consecutive chunks
+};
+__device__ __forceinline__ RowAddr c8s_row(int b, int t, int nch, int P, int T) {
+  const int rows = T / P;
+  RowAddr a;
+  a.chunk_stride = (size_t)P * rows * 8;
+  a.off = (size_t)b * nch * a.chunk_stride + ((size_t)(t % P) * rows + (t / P)) * 8;
+  return a;
+}
+
+// 16 fp32 (+ bias, ELU) -> 8 packed hi words, 8 packed lo words
+__device__ __forceinline__ void bias_elu_split16(const uint32_t (&r)[16], const float* bias, uint32_t (&o)[16]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v0 = elu1(__uint_as_float(r[2 * e]) + bias[2 * e]);
+    const float v1 = elu1(__uint_as_float(r[2 * e + 1]) + bias[2 * e + 1]);
+    split_bf16x2(v0, v1, o[e], o[8 + e]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused ResidualUnit
 // ---------------------------------------------------------------------------------------------
 struct RuParams {
@@ -136,7 +168,7 @@ struct RuCfg {
 };
 
 template <int C>
-__global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuParams p) {
+__global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuParams p) {
   using Cfg = RuCfg<C>;
   constexpr int NCHUNK = Cfg::NCHUNK, KSTEPS = Cfg::KSTEPS, NA = Cfg::NA, NW = Cfg::NW, NBUF = Cfg::NBUF;
   constexpr bool RESIDENT = Cfg::RESIDENT;
@@ -162,9 +194,9 @@ __global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuP
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d1_full[i], 1);
-      mbar_init(&a2_full[i], 4);
+      mbar_init(&a2_full[i], NEW);
       mbar_init(&d2_full[i], 1);
-      mbar_init(&d2_empty[i], 4);
+      mbar_init(&d2_empty[i], NEW);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&w_full[i], 1);
@@ -187,67 +219,91 @@ __global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuP
   auto has = [&](int i) { return i >= 0 && tile_of(i) < p.total_tiles; };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== producer: bulk copies =====================
-      if (RESIDENT) {
-        mbar_arrive_expect_tx(&w_full[0], Cfg::NUNITS * Cfg::UNIT_BYTES);
-        for (int u = 0; u < Cfg::NUNITS; ++u)
-          bulk_copy_g2s(sW + u * Cfg::UNIT_BYTES, p.w + (size_t)u * (Cfg::UNIT_BYTES / 2), Cfg::UNIT_BYTES, &w_full[0]);
+    // ===================== producer =====================
+    // activation tiles: 16-B cp.async by all 32 lanes (the padding rule is just an address per row); weights: bulk copies
+    if (RESIDENT && lane == 0) {
+      mbar_arrive_expect_tx(&w_full[0], Cfg::NUNITS * Cfg::UNIT_BYTES);
+      constexpr int PIECE = 16384;  // few large copies
+      for (int off = 0; off < Cfg::NUNITS * Cfg::UNIT_BYTES; off += PIECE)
+        bulk_copy_g2s(sW + off, reinterpret_cast<const uint8_t*>(p.w) + off,
+                      min(PIECE, Cfg::NUNITS * Cfg::UNIT_BYTES - off), &w_full[0]);
+    }
+    int wstage = 0;
+    uint32_t wphase = 0;
+    auto stream_units = [&](int u0, int u1) {  // lane 0 only
+      for (int u = u0; u < u1; ++u) {
+        mbar_wait(&w_empty[wstage], wphase ^ 1u);
+        mbar_arrive_expect_tx(&w_full[wstage], Cfg::UNIT_BYTES);
+        bulk_copy_g2s(sW + wstage * Cfg::UNIT_BYTES, p.w + (size_t)u * (Cfg::UNIT_BYTES / 2), Cfg::UNIT_BYTES,
+                      &w_full[wstage]);
+        if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
       }
-      int wstage = 0;
-      uint32_t wphase = 0;
-      auto stream_units = [&](int u0, int u1) {
-        for (int u = u0; u < u1; ++u) {
-          mbar_wait(&w_empty[wstage], wphase ^ 1u);
-          mbar_arrive_expect_tx(&w_full[wstage], Cfg::UNIT_BYTES);
-          bulk_copy_g2s(sW + wstage * Cfg::UNIT_BYTES, p.w + (size_t)u * (Cfg::UNIT_BYTES / 2), Cfg::UNIT_BYTES,
-                        &w_full[wstage]);
-          if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
+    };
+    auto issue_a = [&](int i) {
+      const int ab = i % NA;
+      mbar_wait(&a_empty[ab], (((uint32_t)(i / NA)) & 1u) ^ 1u);
+      const int tile = tile_of(i);
+      const int b = tile / p.tiles_per_clip;
+      const int t0 = (tile - b * p.tiles_per_clip) * TILE_M;
+      const int rows = halo + min(TILE_M, p.T - t0);  // smem row r <-> time t0 - halo + r
+      uint8_t* dst = sA + ab * Cfg::A_BYTES;
+      for (int r = lane; r < rows; r += 32) {
+        int tau = t0 - halo + r;
+        uint32_t bytes = 16;
+        if (tau < 0) {  // left padding (soundstream.py:339-344)
+          if (p.pad_mode == 0) tau = -tau;            // reflect, edge sample excluded
+          else if (p.pad_mode == 2) tau = 0;          // replicate
+          else { tau = 0; bytes = 0; }                // constant zero
         }
-      };
-      auto load_a = [&](int i) {
-        const int ab = i % NA;
-        mbar_wait(&a_empty[ab], (((uint32_t)(i / NA)) & 1u) ^ 1u);
-        const int tile = tile_of(i);
-        const int b = tile / p.tiles_per_clip;
-        const int t0 = (tile - b * p.tiles_per_clip) * TILE_M;
-        const int nmain = min(TILE_M, p.T - t0);
-        uint8_t* dst = sA + ab * Cfg::A_BYTES;
-        if (t0 >= halo) {
-          const uint32_t rows = halo + nmain;
-          mbar_arrive_expect_tx(&a_full[ab], 2 * NCHUNK * rows * 16);
-          for (int c = 0; c < 2 * NCHUNK; ++c)
-            bulk_copy_g2s(dst + c * (A_ROWS * 16), p.x + (((size_t)b * 2 * NCHUNK + c) * p.T + (t0 - halo)) * 8,
-                          rows * 16, &a_full[ab]);
+        const __nv_bfloat16* src = p.x + ((size_t)b * 2 * NCHUNK * p.T + tau) * 8;
+#pragma unroll 4
+        for (int c = 0; c < 2 * NCHUNK; ++c)
+          cp_async_16(dst + (c * A_ROWS + r) * 16, src + (size_t)c * p.T * 8, bytes);
+      }
+      cp_async_commit();
+    };
+    // HBM latency under load (3-4 us) exceeds one tile period: pull the tiles PF steps ahead into L2 so that the
+    // cp.async of the staged tile (and the epilogue's skip reads) hit L2
+    constexpr int PF = 3;
+    auto prefetch_tile = [&](int i) {
+      const int tile = tile_of(i);
+      const int b = tile / p.tiles_per_clip;
+      const int t0 = (tile - b * p.tiles_per_clip) * TILE_M;
+      const int first = max(0, t0 - halo), last = min(p.T, t0 + TILE_M);
+      const int lpc = ((last - first) * 16 + 127) / 128 + 1;  // 128-B lines per chunk (+1: unaligned start)
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(p.x + ((size_t)b * 2 * NCHUNK * p.T + first) * 8);
+      const size_t span = (size_t)(last - first) * 16 - 1;
+      for (int idx = lane; idx < 2 * NCHUNK * lpc; idx += 32) {
+        const int c = idx / lpc, l = idx - c * lpc;
+        prefetch_l2(base + (size_t)c * p.T * 16 + min((size_t)l * 128, span));
+      }
+    };
+    if (has(0)) issue_a(0);
+    for (int k = 1; k < PF; ++k)
+      if (has(k)) prefetch_tile(k);
+    for (int i = 0;; ++i) {
+      const bool h1 = has(i), h2 = has(i - (NBUF - 1));
+      if (!h1 && !h2) break;
+      if (h1) {
+        if (has(i + PF)) prefetch_tile(i + PF);
+        if (NA == 2 && has(i + 1)) {
+          issue_a(i + 1);
+          cp_async_wait<1>();
         } else {
-          // first tile(s) of a clip: rows with time < 0 come from the padding rule (soundstream.py:339-344)
-          const int nneg = halo - t0;          // halo rows with negative time
-          const uint32_t rows_pos = t0 + nmain;  // rows with time in [0, t0 + nmain)
-          uint32_t tx = 2 * NCHUNK * (rows_pos + nneg) * 16;
-          mbar_arrive_expect_tx(&a_full[ab], tx);
-          for (int c = 0; c < 2 * NCHUNK; ++c) {
-            const __nv_bfloat16* src = p.x + ((size_t)b * 2 * NCHUNK + c) * p.T * 8;
-            uint8_t* dc = dst + c * (A_ROWS * 16);
-            bulk_copy_g2s(dc + nneg * 16, src, rows_pos * 16, &a_full[ab]);
-            if (p.pad_mode == 0) {
-              for (int u = 1; u <= nneg; ++u)  // time -u  <-  x[u]  (reflect, edge sample excluded)
-                bulk_copy_g2s(dc + (nneg - u) * 16, src + (size_t)u * 8, 16, &a_full[ab]);
-            } else if (p.pad_mode == 2) {
-              for (int u = 1; u <= nneg; ++u) bulk_copy_g2s(dc + (nneg - u) * 16, src, 16, &a_full[ab]);
-            } else {
-              bulk_copy_g2s(dc, g_zero_rows, nneg * 16, &a_full[ab]);
-            }
-          }
+          cp_async_wait<0>();
         }
-      };
-      if (has(0)) load_a(0);
-      for (int i = 0;; ++i) {
-        const bool h1 = has(i), h2 = has(i - (NBUF - 1));
-        if (!h1 && !h2) break;
-        if (NA == 2 && has(i + 1)) load_a(i + 1);
-        if (!RESIDENT && h1) stream_units(0, 7 * KSTEPS);
-        if (NA == 1 && has(i + 1)) load_a(i + 1);
-        if (!RESIDENT && h2) stream_units(7 * KSTEPS, 8 * KSTEPS);
+        fence_proxy_async_smem();  // cp.async writes (generic proxy) -> UMMA operand reads (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[i % NA]);
+          if (!RESIDENT) stream_units(0, 7 * KSTEPS);
+        }
+        __syncwarp();
+        if (NA == 1 && has(i + 1)) issue_a(i + 1);
+      }
+      if (!RESIDENT && h2) {
+        if (lane == 0) stream_units(7 * KSTEPS, 8 * KSTEPS);
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -333,8 +389,9 @@ __global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuP
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: one accumulator row per thread =====================
-    const int q = warp & 3;
+    // ===================== epilogue: one accumulator row per thread, 16-column units split over NSUB warps =====
+    const int ew = warp - 4;
+    const int q = ew & 3, sub = ew >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     for (int i = 0;; ++i) {
@@ -348,26 +405,12 @@ __global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuP
         tc_fence_after_sync();
         const uint32_t d1 = tmem_base + tb * 2 * C + lane_sel;
 #pragma unroll 1
-        for (int g = 0; g < C / 32; ++g) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(d1 + g * 32, r);
+        for (int u = sub; u < KSTEPS; u += NSUB) {
+          uint32_t r[16], o[16];
+          tmem_ld_32x32b_x16(d1 + 16 * u, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[16];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = g * 32 + h * 16 + 2 * e;
-              const float v0 = elu1(__uint_as_float(r[h * 16 + 2 * e]) + sBias[ch]);
-              const float v1 = elu1(__uint_as_float(r[h * 16 + 2 * e + 1]) + sBias[ch + 1]);
-              __nv_bfloat16 h0, l0, h1_, l1;
-              split_bf16(v0, h0, l0);
-              split_bf16(v1, h1_, l1);
-              o[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1_) << 16);
-              o[8 + e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
-            tmem_st_32x32b_x16(d1 + g * 32 + h * 16, o);
-          }
+          bias_elu_split16(r, sBias + 16 * u, o);
+          tmem_st_32x32b_x16(d1 + 16 * u, o);
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -381,40 +424,46 @@ __global__ void __launch_bounds__(256, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuP
         const int b = tile / p.tiles_per_clip;
         const int t = (tile - b * p.tiles_per_clip) * TILE_M + row;
         const bool valid = t < p.T;
+        const __nv_bfloat16* xrow = p.x + ((size_t)b * 2 * NCHUNK * p.T + (valid ? t : 0)) * 8;
+        const RowAddr ya = c8s_row(b, valid ? t : 0, 2 * NCHUNK, p.out_phases, p.T);
+        uint4 xh[2], xl[2];
+        auto load_skip = [&](int u) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            xh[c] = __ldg(reinterpret_cast<const uint4*>(xrow + (size_t)(2 * u + c) * p.T * 8));
+            xl[c] = __ldg(reinterpret_cast<const uint4*>(xrow + (size_t)(NCHUNK + 2 * u + c) * p.T * 8));
+          }
+        };
+        if (sub < KSTEPS) load_skip(sub);  // in flight while we wait for the accumulator
         mbar_wait(&d2_full[tb], ((uint32_t)(i2 / NBUF)) & 1u);
         tc_fence_after_sync();
         const uint32_t d2 = tmem_base + tb * 2 * C + C + lane_sel;
 #pragma unroll 1
-        for (int g = 0; g < C / 32; ++g) {
-          uint4 xh[4], xl[4];
-          if (valid) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              xh[c] = __ldg(reinterpret_cast<const uint4*>(p.x + (((size_t)b * 2 * NCHUNK + g * 4 + c) * p.T + t) * 8));
-              xl[c] = __ldg(
-                  reinterpret_cast<const uint4*>(p.x + (((size_t)b * 2 * NCHUNK + NCHUNK + g * 4 + c) * p.T + t) * 8));
-            }
-          }
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(d2 + g * 32, r);
+        for (int u = sub; u < KSTEPS; u += NSUB) {
+          const uint4 ch[2] = {xh[0], xh[1]}, cl[2] = {xl[0], xl[1]};
+          if (u + NSUB < KSTEPS) load_skip(u + NSUB);
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(d2 + 16 * u, r);
           tmem_ld_wait();
-          if (valid) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t hw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
-              const uint32_t lw[4] = {xl[c].x, xl[c].y, xl[c].z, xl[c].w};
-              float v[8];
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t hw[4] = {ch[c].x, ch[c].y, ch[c].z, ch[c].w};
+            const uint32_t lw[4] = {cl[c].x, cl[c].y, cl[c].z, cl[c].w};
+            uint32_t oh[4], ol[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int ch = g * 32 + c * 8 + e;
-                const float xs = (e & 1) ? (bf16_hi(hw[e >> 1]) + bf16_hi(lw[e >> 1]))
-                                         : (bf16_lo(hw[e >> 1]) + bf16_lo(lw[e >> 1]));
-                v[e] = xs + elu1(__uint_as_float(r[c * 8 + e]) + sBias[C + ch]);
-              }
-              uint4 hi, lo;
-              split8(v, hi, lo);
-              *reinterpret_cast<uint4*>(p.y + c8s_off(b, g * 4 + c, t, 2 * NCHUNK, p.out_phases, p.T)) = hi;
-              *reinterpret_cast<uint4*>(p.y + c8s_off(b, NCHUNK + g * 4 + c, t, 2 * NCHUNK, p.out_phases, p.T)) = lo;
+            for (int e = 0; e < 4; ++e) {
+              const int chn = 16 * u + 8 * c + 2 * e;
+              const float x0 = bf16_lo(hw[e]) + bf16_lo(lw[e]);
+              const float x1 = bf16_hi(hw[e]) + bf16_hi(lw[e]);
+              const float v0 = x0 + elu1(__uint_as_float(r[8 * c + 2 * e]) + sBias[C + chn]);
+              const float v1 = x1 + elu1(__uint_as_float(r[8 * c + 2 * e + 1]) + sBias[C + chn + 1]);
+              split_bf16x2(v0, v1, oh[e], ol[e]);
+            }
+            if (valid) {
+              *reinterpret_cast<uint4*>(p.y + ya.off + (size_t)(2 * u + c) * ya.chunk_stride) =
+                  make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4*>(p.y + ya.off + (size_t)(NCHUNK + 2 * u + c) * ya.chunk_stride) =
+                  make_uint4(ol[0], ol[1], ol[2], ol[3]);
             }
           }
         }
@@ -442,19 +491,18 @@ static int launch_ru(const RuParams& p, cudaStream_t stream) {
   }
   const int ctas_per_sm = (Cfg::SMEM_BYTES <= 110 * 1024 && 2 * Cfg::TMEM_COLS <= 512) ? 2 : 1;
   const int grid = min(p.total_tiles, num_sms() * ctas_per_sm);
-  kfn<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  kfn<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;
 }
 
-
 // ---------------------------------------------------------------------------------------------
 // plain / strided causal conv (dilation 1) as a pipelined implicit GEMM
 //   out[t, co] = b[co] + sum_{j < K} sum_ci W[co, ci, j] xp[ci, t*s + j],  xp[u] = x[u - (K - s)]  (soundstream.py:332-345)
 // Input: C8S with P = s phase planes, so tap j of output row t reads plane ((j - pad) mod s), row t + floor((j - pad) / s):
-// unit-stride rows for every tap.  One pipeline stage = one (tap, 16-channel k-step) unit: A hi/lo [2][128][16 B] each,
-// W hi/lo [2][BN][16 B] each; three MMAs per stage.
+// unit-stride rows for every tap.  One pipeline stage = one (tap, 16-channel k-step) unit: A hi/lo [2][128][16 B] each
+// (cp.async, 16 B per lane), W hi/lo [2][BN][16 B] each (one bulk copy); three MMAs per stage.
 // ---------------------------------------------------------------------------------------------
 struct ConvParams {
   const __nv_bfloat16* x;   // C8S [B][2 Cin/8][s][Tin/s][8]
@@ -471,18 +519,19 @@ struct ConvCfg {
   static constexpr int W_BYTES = 4 * BN * 16;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = BN == 256 ? 8 : 10;
+  static constexpr int LOOKAHEAD = 5;                   // cp.async groups in flight before the oldest is published
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + 128;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParams p) {
   using Cfg = ConvCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES, LA = Cfg::LOOKAHEAD;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* full = bars;                  // [STAGES]  count 2: W bulk copy (expect_tx) + A (cp.async groups)
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES; // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
@@ -490,12 +539,12 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const ConvParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], 2);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], NEW);
     }
     fence_mbar_init();
   }
@@ -519,50 +568,95 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const ConvParams p) {
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int b, mt, nt;
-        decode(tile, b, mt, nt);
-        const int t0 = mt * TILE_M;
-        const int nrows = min(TILE_M, p.n_out - t0);
-        for (int j = 0; j < p.K; ++j) {
-          const int q = j - pad;
-          const int plane = ((q % p.s) + p.s) % p.s;
-          const int shift = (q - plane) / p.s;   // floor(q / s)
-          // rows of this tile whose source row is negative (left padding)
-          const int nneg = min(nrows, max(0, -(t0 + shift)));
-          for (int kk = 0; kk < ksteps; ++kk) {
-            mbar_wait(&empty[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sw = sa + Cfg::A_BYTES;
-            mbar_arrive_expect_tx(&full[stage], 4 * nrows * 16 + Cfg::W_BYTES);
-            for (int part = 0; part < 2; ++part)
-              for (int cc = 0; cc < 2; ++cc) {
-                const int c = part * nch + 2 * kk + cc;
-                const __nv_bfloat16* plane0 = p.x + (((size_t)b * 2 * nch + c) * p.s) * (size_t)rows_in * 8;
-                uint8_t* dst = sa + (part * 2 + cc) * (TILE_M * 16);
-                if (nrows > nneg)
-                  bulk_copy_g2s(dst + nneg * 16, plane0 + ((size_t)plane * rows_in + (t0 + nneg + shift)) * 8,
-                                (nrows - nneg) * 16, &full[stage]);
-                for (int r = 0; r < nneg; ++r) {
-                  // x index u = (t0 + r) * s + q < 0: reflect -> x[-u]; replicate -> x[0]; constant -> 0
-                  const int u = (t0 + r) * p.s + q;
-                  const __nv_bfloat16* src;
-                  if (p.pad_mode == 0) src = plane0 + ((size_t)((-u) % p.s) * rows_in + (-u) / p.s) * 8;
-                  else if (p.pad_mode == 2) src = plane0;
-                  else src = reinterpret_cast<const __nv_bfloat16*>(g_zero_rows);
-                  bulk_copy_g2s(dst + r * 16, src, 16, &full[stage]);
-                }
+    // ===================== producer (all 32 lanes) =====================
+    int stage = 0, done_stage = 0, pending = 0;
+    uint32_t phase = 0;
+    auto publish_oldest = [&]() {  // the oldest cp.async group has landed: make it visible to the UMMA, signal
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[done_stage]);
+      if (++done_stage == STAGES) done_stage = 0;
+      --pending;
+    };
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int b, mt, nt;
+      decode(tile, b, mt, nt);
+      const int t0 = mt * TILE_M;
+      const int nrows = min(TILE_M, p.n_out - t0);
+      const __nv_bfloat16* xb = p.x + (size_t)b * 2 * nch * p.s * (size_t)rows_in * 8;
+      {
+        // the stage ring holds ~1 us of MMA work, less than the HBM latency under load: pull the NEXT tile's input rows
+        // (every plane, every chunk) into L2 while this tile streams
+        const int ntile = tile + (int)gridDim.x;
+        if (ntile < p.total_tiles) {
+          int nb, nmt, nnt;
+          decode(ntile, nb, nmt, nnt);
+          if (nnt == 0 || p.n_tiles == 1) {
+            const int r0 = max(0, nmt * TILE_M - 2), r1 = min(rows_in, nmt * TILE_M + TILE_M + 1);
+            const int lpc = ((r1 - r0) * 16 + 127) / 128 + 1;
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(p.x + ((size_t)nb * 2 * nch * p.s * (size_t)rows_in + r0) * 8);
+            const size_t span = (size_t)(r1 - r0) * 16 - 1;
+            const int planes = 2 * nch * p.s;
+            for (int idx = lane; idx < planes * lpc; idx += 32) {
+              const int pl = idx / lpc, l = idx - pl * lpc;
+              prefetch_l2(base + (size_t)pl * rows_in * 16 + min((size_t)l * 128, span));
+            }
+          }
+        }
+      }
+      for (int j = 0; j < p.K; ++j) {
+        const int q = j - pad;
+        const int plane = ((q % p.s) + p.s) % p.s;
+        const int shift = (q - plane) / p.s;   // floor(q / s)
+        // per-lane source rows of this tap (row r of the tile -> x row, or the padding rule when it is negative)
+        size_t src_row[TILE_M / 32];
+        uint32_t src_bytes[TILE_M / 32];
+#pragma unroll
+        for (int it = 0; it < TILE_M / 32; ++it) {
+          const int r = it * 32 + lane;
+          int pl = plane, rw = t0 + r + shift;
+          uint32_t bytes = 16;
+          if (rw < 0) {  // x index u = (t0 + r) * s + q < 0
+            const int u = (t0 + r) * p.s + q;
+            if (p.pad_mode == 0) { pl = (-u) % p.s; rw = (-u) / p.s; }   // reflect
+            else if (p.pad_mode == 2) { pl = 0; rw = 0; }                 // replicate
+            else { pl = 0; rw = 0; bytes = 0; }                           // constant zero
+          }
+          src_row[it] = ((size_t)pl * rows_in + rw) * 8;
+          src_bytes[it] = bytes;
+        }
+        for (int kk = 0; kk < ksteps; ++kk) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int part = 0; part < 2; ++part)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = part * nch + 2 * kk + cc;
+              const __nv_bfloat16* plane0 = xb + (size_t)c * p.s * (size_t)rows_in * 8;
+              uint8_t* dst = sa + (part * 2 + cc) * (TILE_M * 16);
+#pragma unroll
+              for (int it = 0; it < TILE_M / 32; ++it) {
+                const int r = it * 32 + lane;
+                if (r < nrows) cp_async_16(dst + r * 16, plane0 + src_row[it], src_bytes[it]);
               }
-            bulk_copy_g2s(sw, p.w + (((size_t)nt * p.K + j) * ksteps + kk) * (size_t)(Cfg::W_BYTES / 2), Cfg::W_BYTES,
-                          &full[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          cp_async_commit();
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::W_BYTES);
+            bulk_copy_g2s(sa + Cfg::A_BYTES, p.w + (((size_t)nt * p.K + j) * ksteps + kk) * (size_t)(Cfg::W_BYTES / 2),
+                          Cfg::W_BYTES, &full[stage]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++pending > LA) {
+            cp_async_wait<LA>();
+            publish_oldest();
           }
         }
       }
     }
+    cp_async_wait<0>();
+    while (pending > 0) publish_oldest();
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, BN, false, false);
@@ -593,58 +687,57 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const ConvParams p) {
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int ew = warp - 4;
+    const int q = ew & 3, sub = ew >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int nch_out = p.Cout / 8;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
       int b, mt, nt;
       decode(tile, b, mt, nt);
       const int acc = iter & 1;
-      mbar_wait(&acc_full[acc], ((uint32_t)(iter >> 1)) & 1u);
-      tc_fence_after_sync();
       const int t = mt * TILE_M + row;
       const bool valid = t < p.n_out;
       const int n0 = nt * BN;
+      const RowAddr ya = c8s_row(b, valid ? t : 0, 2 * nch_out, p.out_fp32 ? 1 : p.out_phases, p.n_out);
+      mbar_wait(&acc_full[acc], ((uint32_t)(iter >> 1)) & 1u);
+      tc_fence_after_sync();
       const uint32_t d = tmem_base + acc * BN + lane_sel;
-      const int nch_out = p.Cout / 8;
 #pragma unroll 1
-      for (int g = 0; g < BN / 32; ++g) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld_32x32b_x32(d + g * 32, r);
+      for (int g = sub; g < BN / 16; g += NSUB) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(d + g * 16, r);
         tmem_ld_wait();
-        if (g == BN / 32 - 1) {
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-        const int ch0 = n0 + g * 32;
-        if (valid && ch0 < p.Cout) {
-          float v[32];
+        const int ch0 = n0 + g * 16;
+        float v[16];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + (p.bias ? __ldg(p.bias + ch0 + e) : 0.f);
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) + (p.bias ? __ldg(p.bias + ch0 + e) : 0.f);
+        if (valid) {
           if (p.out_fp32) {
             float* dst = reinterpret_cast<float*>(p.y) + ((size_t)b * p.n_out + t) * p.Cout + ch0;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4)
+            for (int e = 0; e < 16; e += 4)
               *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
           } else {
             __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float v8[8];
+            for (int c = 0; c < 2; ++c) {
+              uint32_t oh[4], ol[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v8[e] = v[c * 8 + e];
-              uint4 hi, lo;
-              split8(v8, hi, lo);
+              for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], oh[e], ol[e]);
               const int chunk = ch0 / 8 + c;
-              *reinterpret_cast<uint4*>(yb + c8s_off(b, chunk, t, 2 * nch_out, p.out_phases, p.n_out)) = hi;
-              *reinterpret_cast<uint4*>(yb + c8s_off(b, nch_out + chunk, t, 2 * nch_out, p.out_phases, p.n_out)) = lo;
+              *reinterpret_cast<uint4*>(yb + ya.off + (size_t)chunk * ya.chunk_stride) =
+                  make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4*>(yb + ya.off + (size_t)(nch_out + chunk) * ya.chunk_stride) =
+                  make_uint4(ol[0], ol[1], ol[2], ol[3]);
             }
           }
         }
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
   }
   tc_fence_before_sync();
@@ -663,7 +756,7 @@ static int launch_conv(const ConvParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = min(p.total_tiles, num_sms());
-  kfn<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  kfn<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;

@@ -533,7 +533,10 @@ def codec_ru_tc(x, w_units, b7, b1, *, dilation, pad_mode="reflect", out_phases=
     assert P == 1 and x.dtype == bf16 and x.is_contiguous() and w_units.dtype == bf16 and w_units.is_contiguous()
     assert w_units.numel() == 8 * (C // 16) * 2 * 2 * C * 8
     y = torch.empty(B, nch2, out_phases, T // out_phases, 8, device=x.device, dtype=bf16)
-    with _timed("codec_ru_tc", 2.0 * B * C * T * 4, "byte"):
+    cls = "codec_ru_tc"
+    if _PROFILE is not None and PROFILE_SHAPES:
+        cls += f" C{C} T{T} d{dilation} P{out_phases}"
+    with _timed(cls, 2.0 * B * C * T * 4, "byte"):
         _lib.call("alm_codec_ru_tc", x, y, w_units, b7, b1, B, C, T, int(dilation), PAD_MODES[pad_mode],
                   int(out_phases))
     return y
@@ -550,7 +553,10 @@ def codec_conv_tc(x, w_units, bias, *, cout, kernel_size, stride, pad_mode="refl
         y = torch.empty(B, n_out, cout, device=x.device, dtype=f32)
     else:
         y = torch.empty(B, 2 * cout // 8, out_phases, n_out // out_phases, 8, device=x.device, dtype=bf16)
-    with _timed("codec_conv_tc", 4.0 * B * (Cin * Tin + cout * n_out), "byte"):
+    cls = "codec_conv_tc"
+    if _PROFILE is not None and PROFILE_SHAPES:
+        cls += f" Cin{Cin} Cout{cout} K{kernel_size} s{stride} T{Tin}"
+    with _timed(cls, 4.0 * B * (Cin * Tin + cout * n_out), "byte"):
         _lib.call("alm_codec_conv_tc", x, y, w_units, bias, B, Cin, cout, Tin, int(kernel_size), int(stride),
                   PAD_MODES[pad_mode], int(out_phases), int(out_fp32))
     return y
