@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
+    *os.environ.get("ALM_EXTRA_NVCC_FLAGS", "").split(),  # e.g. -DALM_RU_TRACE for tools/ru_trace.py
 ]
 
 

@@ -33,11 +33,22 @@
 namespace alm {
 namespace ctc {
 
-__device__ uint4 g_zero_rows[64];  // 1 KB of zeros (static storage): source of constant-padding halo rows
+__device__ uint4 g_zero_rows[64];
+#ifdef ALM_RU_TRACE
+// wait-time accounting of the MMA issuer / one epilogue warp (cycles summed over CTAs): build with -DALM_RU_TRACE
+__device__ unsigned long long g_ru_trace[16];
+#define RU_TRACE_WAIT(slot, stmt)                                  \
+  do {                                                             \
+    const long long _t = clock64();                                \
+    stmt;                                                          \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_ru_trace[slot], (unsigned long long)(clock64() - _t)); \
+  } while (0)
+#else
+#define RU_TRACE_WAIT(slot, stmt) stmt
+#endif  // 1 KB of zeros (static storage): source of constant-padding halo rows
 
 constexpr int TILE_M = 128;
 constexpr int MAX_HALO = 54;  // 6 * dilation 9
-constexpr int A_ROWS = TILE_M + MAX_HALO;
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : (__expf(v) - 1.f); }
 
@@ -150,6 +161,8 @@ struct RuParams {
   const float* b1;
   int B, T, d, pad_mode, out_phases;
   int tiles_per_clip, total_tiles;
+  int ar;      // rows of one staged chunk: 128 + 6 d
+  int na, nw;  // staged activation tiles (1 or 2), weight ring stages (streamed mode)
 };
 
 template <int C>
@@ -158,25 +171,26 @@ struct RuCfg {
   static constexpr int KSTEPS = C / 16;
   static constexpr bool RESIDENT = C <= 64;       // all weights stay in shared memory for the CTA's lifetime
   static constexpr int NBUF = C <= 128 ? 2 : 1;   // tiles in flight in tensor memory (each: D1 | D2 = 2C columns)
-  static constexpr int NA = C <= 128 ? 2 : 1;     // staged activation tiles
-  static constexpr int A_BYTES = 2 * NCHUNK * A_ROWS * 16;
   static constexpr int UNIT_BYTES = 2 * 2 * C * 16;  // hi [2 chunks][C][16 B] + lo
   static constexpr int NUNITS = 8 * KSTEPS;
-  static constexpr int NW = RESIDENT ? NUNITS : (C == 128 ? 4 : 2);
+  static constexpr int MAX_NW = 16;
   static constexpr int TMEM_COLS = NBUF * 2 * C;
-  static constexpr int SMEM_BYTES = NA * A_BYTES + NW * UNIT_BYTES + 2 * C * 4 + 512 + 128;
+  static constexpr int FIXED_BYTES = 2 * C * 4 + 512 + 128;  // biases, barriers, alignment slack
+  static constexpr int MAX_SMEM = 232448;
 };
 
 template <int C>
 __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuParams p) {
   using Cfg = RuCfg<C>;
-  constexpr int NCHUNK = Cfg::NCHUNK, KSTEPS = Cfg::KSTEPS, NA = Cfg::NA, NW = Cfg::NW, NBUF = Cfg::NBUF;
+  constexpr int NCHUNK = Cfg::NCHUNK, KSTEPS = Cfg::KSTEPS, NBUF = Cfg::NBUF;
   constexpr bool RESIDENT = Cfg::RESIDENT;
+  const int NA = p.na, NW = p.nw, A_ROWS = p.ar;
+  const int A_BYTES = 2 * NCHUNK * A_ROWS * 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* sA = smem;
-  uint8_t* sW = sA + NA * Cfg::A_BYTES;
-  float* sBias = reinterpret_cast<float*>(sW + NW * Cfg::UNIT_BYTES);
+  uint8_t* sW = sA + NA * A_BYTES;
+  float* sBias = reinterpret_cast<float*>(sW + (RESIDENT ? Cfg::NUNITS : NW) * Cfg::UNIT_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * C);
   uint64_t* a_full = bars;              // [2]
   uint64_t* a_empty = bars + 2;         // [2]
@@ -184,9 +198,9 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
   uint64_t* a2_full = bars + 6;         // [2]
   uint64_t* d2_full = bars + 8;         // [2]
   uint64_t* d2_empty = bars + 10;       // [2]
-  uint64_t* w_full = bars + 12;         // [<= 4] (resident: [0] only)
-  uint64_t* w_empty = bars + 16;        // [<= 4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* w_full = bars + 12;         // [<= 16] (resident: [0] only)
+  uint64_t* w_empty = bars + 28;        // [<= 16]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
       mbar_init(&d2_full[i], 1);
       mbar_init(&d2_empty[i], NEW);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < Cfg::MAX_NW; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
       const int b = tile / p.tiles_per_clip;
       const int t0 = (tile - b * p.tiles_per_clip) * TILE_M;
       const int rows = halo + min(TILE_M, p.T - t0);  // smem row r <-> time t0 - halo + r
-      uint8_t* dst = sA + ab * Cfg::A_BYTES;
+      uint8_t* dst = sA + ab * A_BYTES;
       for (int r = lane; r < rows; r += 32) {
         int tau = t0 - halo + r;
         uint32_t bytes = 16;
@@ -286,19 +300,16 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
       if (!h1 && !h2) break;
       if (h1) {
         if (has(i + PF)) prefetch_tile(i + PF);
-        if (NA == 2 && has(i + 1)) {
-          issue_a(i + 1);
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
-        }
+        cp_async_wait<0>();        // tile i (issued one step ago)
         fence_proxy_async_smem();  // cp.async writes (generic proxy) -> UMMA operand reads (async proxy)
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&a_full[i % NA]);
-          if (!RESIDENT) stream_units(0, 7 * KSTEPS);
+        if (lane == 0) mbar_arrive(&a_full[i % NA]);
+        // publish tile i BEFORE staging tile i + 1: the staging waits for a_empty and takes ~1 k clk of issue
+        if (NA == 2 && has(i + 1)) issue_a(i + 1);
+        if (!RESIDENT) {
+          if (lane == 0) stream_units(0, 7 * KSTEPS);
+          __syncwarp();
         }
-        __syncwarp();
         if (NA == 1 && has(i + 1)) issue_a(i + 1);
       }
       if (!RESIDENT && h2) {
@@ -307,9 +318,12 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    {
+      // ===================== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =======
       constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, C, false, false);
+#ifdef ALM_RU_TRACE
+      const long long t_begin = clock64();
+#endif
       if (RESIDENT) mbar_wait(&w_full[0], 0);
       int wstage = 0;
       uint32_t wphase = 0;
@@ -320,73 +334,93 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
         if (!h1 && !h2) break;
         if (h1) {
           const int ab = i % NA, tb = i % NBUF;
-          mbar_wait(&a_full[ab], ((uint32_t)(i / NA)) & 1u);
+          RU_TRACE_WAIT(0, mbar_wait(&a_full[ab], ((uint32_t)(i / NA)) & 1u));
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(sA + ab * Cfg::A_BYTES);
+          const uint32_t a_addr = smem_u32(sA + ab * A_BYTES);
           const uint32_t d1 = tmem_base + tb * 2 * C;
-          for (int j = 0; j < 7; ++j) {
-            const uint32_t row_off = (uint32_t)(j * p.d) * 16u;
+          // descriptors are built once; between MMAs only the 14-bit start-address field (>> 4) of the low word moves
+          // (tools/mma_bench.cu: with the issue path this lean an N <= 64 MMA retires every ~45 clk, N = 128 / 256 at
+          // their 64 / 128 clk floors; rebuilding descriptors per MMA costs several times that)
+          const uint64_t a_hi0 = umma_smem_desc_nosw(a_addr, 128, A_ROWS * 16);
+          const uint64_t a_lo0 = umma_smem_desc_nosw(a_addr + NCHUNK * (A_ROWS * 16), 128, A_ROWS * 16);
+          const uint64_t b0 = umma_smem_desc_nosw(sw_addr, 128, C * 16);
+          const uint32_t kstep_units = 2 * A_ROWS;       // two chunks, in 16-B units
 #pragma unroll 1
+          for (int j = 0; j < 7; ++j) {
+            const uint32_t row_units = (uint32_t)(j * p.d);
+#pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
               const int u = j * KSTEPS + kk;
-              uint32_t wb;
+              uint32_t w_units;  // offset of this unit's weights from sW, in 16-B units
               if (RESIDENT) {
-                wb = sw_addr + u * Cfg::UNIT_BYTES;
+                w_units = u * (Cfg::UNIT_BYTES / 16);
               } else {
-                mbar_wait(&w_full[wstage], wphase);
+                RU_TRACE_WAIT(3, mbar_wait(&w_full[wstage], wphase));
                 tc_fence_after_sync();
-                wb = sw_addr + wstage * Cfg::UNIT_BYTES;
+                w_units = wstage * (Cfg::UNIT_BYTES / 16);
               }
-              const uint64_t a_hi = umma_smem_desc_nosw(a_addr + (2 * kk) * (A_ROWS * 16) + row_off, 128, A_ROWS * 16);
-              const uint64_t a_lo =
-                  umma_smem_desc_nosw(a_addr + (NCHUNK + 2 * kk) * (A_ROWS * 16) + row_off, 128, A_ROWS * 16);
-              const uint64_t b_hi = umma_smem_desc_nosw(wb, 128, C * 16);
-              const uint64_t b_lo = umma_smem_desc_nosw(wb + 2 * C * 16, 128, C * 16);
-              umma_bf16_ss(d1, a_hi, b_hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
-              umma_bf16_ss(d1, a_lo, b_hi, idesc, 1u);
-              umma_bf16_ss(d1, a_hi, b_lo, idesc, 1u);
+              const uint64_t a_hi = a_hi0 + (uint64_t)(kk * kstep_units + row_units);
+              const uint64_t a_lo = a_lo0 + (uint64_t)(kk * kstep_units + row_units);
+              const uint64_t b_hi = b0 + (uint64_t)w_units;
+              const uint64_t b_lo = b_hi + (uint64_t)(2 * C);
+              if (elect_one_sync()) {
+                umma_bf16_ss(d1, a_hi, b_hi, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_bf16_ss(d1, a_lo, b_hi, idesc, 1u);
+                umma_bf16_ss(d1, a_hi, b_lo, idesc, 1u);
+                if (!RESIDENT) umma_commit(&w_empty[wstage]);
+              }
               if (!RESIDENT) {
-                umma_commit(&w_empty[wstage]);
                 if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
               }
             }
           }
-          umma_commit(&a_empty[ab]);  // the staged tile may be overwritten once these MMAs have read it
-          umma_commit(&d1_full[tb]);
+          if (elect_one_sync()) {
+            umma_commit(&a_empty[ab]);  // the staged tile may be overwritten once these MMAs have read it
+            umma_commit(&d1_full[tb]);
+          }
         }
         if (h2) {
           const int tb = i2 % NBUF;
           const uint32_t ph = ((uint32_t)(i2 / NBUF)) & 1u;
-          mbar_wait(&a2_full[tb], ph);
-          mbar_wait(&d2_empty[tb], ph ^ 1u);
+          RU_TRACE_WAIT(1, mbar_wait(&a2_full[tb], ph));
+          RU_TRACE_WAIT(2, mbar_wait(&d2_empty[tb], ph ^ 1u));
           tc_fence_after_sync();
           const uint32_t d1 = tmem_base + tb * 2 * C;
           const uint32_t d2 = d1 + C;
-#pragma unroll 1
+          const uint64_t b0 = umma_smem_desc_nosw(sw_addr, 128, C * 16);
+#pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk) {
             const int u = 7 * KSTEPS + kk;
-            uint32_t wb;
+            uint32_t w_units;
             if (RESIDENT) {
-              wb = sw_addr + u * Cfg::UNIT_BYTES;
+              w_units = u * (Cfg::UNIT_BYTES / 16);
             } else {
               mbar_wait(&w_full[wstage], wphase);
               tc_fence_after_sync();
-              wb = sw_addr + wstage * Cfg::UNIT_BYTES;
+              w_units = wstage * (Cfg::UNIT_BYTES / 16);
             }
-            const uint64_t b_hi = umma_smem_desc_nosw(wb, 128, C * 16);
-            const uint64_t b_lo = umma_smem_desc_nosw(wb + 2 * C * 16, 128, C * 16);
+            const uint64_t b_hi = b0 + (uint64_t)w_units;
+            const uint64_t b_lo = b_hi + (uint64_t)(2 * C);
             // A operand of k-step kk sits where E1 left it: hi pairs in columns [16 kk, 16 kk + 8), lo in the next 8
-            umma_bf16_ts(d2, d1 + 16 * kk, b_hi, idesc, kk > 0 ? 1u : 0u);
-            umma_bf16_ts(d2, d1 + 16 * kk + 8, b_hi, idesc, 1u);
-            umma_bf16_ts(d2, d1 + 16 * kk, b_lo, idesc, 1u);
+            if (elect_one_sync()) {
+              umma_bf16_ts(d2, d1 + 16 * kk, b_hi, idesc, kk > 0 ? 1u : 0u);
+              umma_bf16_ts(d2, d1 + 16 * kk + 8, b_hi, idesc, 1u);
+              umma_bf16_ts(d2, d1 + 16 * kk, b_lo, idesc, 1u);
+              if (!RESIDENT) umma_commit(&w_empty[wstage]);
+            }
             if (!RESIDENT) {
-              umma_commit(&w_empty[wstage]);
               if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
             }
           }
-          umma_commit(&d2_full[tb]);
+          if (elect_one_sync()) umma_commit(&d2_full[tb]);
         }
       }
+#ifdef ALM_RU_TRACE
+      if (lane == 0) {
+        atomicAdd(&g_ru_trace[8], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&g_ru_trace[9], 1ull);
+      }
+#endif
     }
   } else if (warp >= 4) {
     // ===================== epilogue: one accumulator row per thread, 16-column units split over NSUB warps =====
@@ -401,7 +435,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
       if (h1) {
         // ---- E1: D1 -> (+b7, ELU, split) -> the same columns as the packed bf16 A operand of the 1x1 conv ----
         const int tb = i % NBUF;
-        mbar_wait(&d1_full[tb], ((uint32_t)(i / NBUF)) & 1u);
+        if (warp == 4 && lane == 0) { RU_TRACE_WAIT(4, mbar_wait(&d1_full[tb], ((uint32_t)(i / NBUF)) & 1u)); } else mbar_wait(&d1_full[tb], ((uint32_t)(i / NBUF)) & 1u);
         tc_fence_after_sync();
         const uint32_t d1 = tmem_base + tb * 2 * C + lane_sel;
 #pragma unroll 1
@@ -435,7 +469,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
           }
         };
         if (sub < KSTEPS) load_skip(sub);  // in flight while we wait for the accumulator
-        mbar_wait(&d2_full[tb], ((uint32_t)(i2 / NBUF)) & 1u);
+        if (warp == 4 && lane == 0) { RU_TRACE_WAIT(5, mbar_wait(&d2_full[tb], ((uint32_t)(i2 / NBUF)) & 1u)); } else mbar_wait(&d2_full[tb], ((uint32_t)(i2 / NBUF)) & 1u);
         tc_fence_after_sync();
         const uint32_t d2 = tmem_base + tb * 2 * C + C + lane_sel;
 #pragma unroll 1
@@ -481,17 +515,36 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
 }
 
 template <int C>
-static int launch_ru(const RuParams& p, cudaStream_t stream) {
+static int launch_ru(RuParams p, cudaStream_t stream) {
   using Cfg = RuCfg<C>;
   auto kfn = ru_tc_kernel<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ALM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+  p.ar = TILE_M + 6 * p.d;
+  const int a_bytes = 2 * Cfg::NCHUNK * p.ar * 16;
+  int smem;
+  if (Cfg::RESIDENT) {
+    p.na = 2;
+    p.nw = 0;
+    smem = 2 * a_bytes + Cfg::NUNITS * Cfg::UNIT_BYTES + Cfg::FIXED_BYTES;
+  } else {
+    // the weight ring must cover ~1 us of L2 latency at ~42 B/clk of consumption (~70 KB): as many stages as fit; a
+    // second staged activation tile only if that still leaves at least 48 KB of ring
+    auto stages = [&](int na) {
+      return min(Cfg::MAX_NW, (Cfg::MAX_SMEM - na * a_bytes - Cfg::FIXED_BYTES) / Cfg::UNIT_BYTES);
+    };
+    p.na = (Cfg::NBUF == 2 && stages(2) * Cfg::UNIT_BYTES >= 48 * 1024) ? 2 : 1;
+    p.nw = stages(p.na);
+    if (p.nw < 2) return ALM_ERR_UNSUPPORTED;
+    smem = p.na * a_bytes + p.nw * Cfg::UNIT_BYTES + Cfg::FIXED_BYTES;
   }
-  const int ctas_per_sm = (Cfg::SMEM_BYTES <= 110 * 1024 && 2 * Cfg::TMEM_COLS <= 512) ? 2 : 1;
+  if (smem > Cfg::MAX_SMEM) return ALM_ERR_UNSUPPORTED;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    ALM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int ctas_per_sm = (smem <= 110 * 1024 && 2 * Cfg::TMEM_COLS <= 512) ? 2 : 1;
   const int grid = min(p.total_tiles, num_sms() * ctas_per_sm);
-  kfn<<<grid, CTA_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  kfn<<<grid, CTA_THREADS, smem, stream>>>(p);
   ALM_CHECK_LAUNCH();
   ALM_LAUNCHED(1);
   return ALM_OK;
@@ -658,11 +711,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParam
     cp_async_wait<0>();
     while (pending > 0) publish_oldest();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(TILE_M, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      // descriptors built once; per stage only the start-address field moves (see ru_tc_kernel)
+      const uint64_t a0 = umma_smem_desc_nosw(smem_u32(smem), 128, TILE_M * 16);
+      const uint64_t b0 = umma_smem_desc_nosw(smem_u32(smem) + Cfg::A_BYTES, 128, BN * 16);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
         const int acc = iter & 1;
         mbar_wait(&acc_empty[acc], (((uint32_t)(iter >> 1)) & 1u) ^ 1u);
@@ -671,19 +727,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParam
         for (int u = 0; u < units; ++u) {
           mbar_wait(&full[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sw = sa + Cfg::A_BYTES;
-          const uint64_t a_hi = umma_smem_desc_nosw(sa, 128, TILE_M * 16);
-          const uint64_t a_lo = umma_smem_desc_nosw(sa + 2 * TILE_M * 16, 128, TILE_M * 16);
-          const uint64_t b_hi = umma_smem_desc_nosw(sw, 128, BN * 16);
-          const uint64_t b_lo = umma_smem_desc_nosw(sw + 2 * BN * 16, 128, BN * 16);
-          umma_bf16_ss(d, a_hi, b_hi, idesc, u > 0 ? 1u : 0u);
-          umma_bf16_ss(d, a_lo, b_hi, idesc, 1u);
-          umma_bf16_ss(d, a_hi, b_lo, idesc, 1u);
-          umma_commit(&empty[stage]);
+          const uint64_t off = (uint64_t)(stage * (Cfg::STAGE_BYTES / 16));
+          const uint64_t a_hi = a0 + off, a_lo = a_hi + 2 * TILE_M;
+          const uint64_t b_hi = b0 + off, b_lo = b_hi + 2 * BN;
+          if (elect_one_sync()) {
+            umma_bf16_ss(d, a_hi, b_hi, idesc, u > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, idesc, 1u);
+            umma_bf16_ss(d, a_hi, b_lo, idesc, 1u);
+            umma_commit(&empty[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&acc_full[acc]);
+        if (elect_one_sync()) umma_commit(&acc_full[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -835,3 +890,15 @@ extern "C" int alm_codec_conv_tc(const void* x, void* y, const void* w_units, co
   if (BN == 128) return ctc::launch_conv<128>(p, stream);
   return ctc::launch_conv<64>(p, stream);
 }
+
+#ifdef ALM_RU_TRACE
+extern "C" int alm_debug_ru_trace(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, alm::ctc::g_ru_trace, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(alm::ctc::g_ru_trace, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

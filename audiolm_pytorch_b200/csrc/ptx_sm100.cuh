@@ -212,6 +212,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // ---------------------------------------------------------------------------------------------
 // additions for the codec tensor-core kernels (codec_tc.cu)
 // ---------------------------------------------------------------------------------------------
+// true in exactly one lane of a fully converged warp.  tcgen05.mma / commit issued as `if (elect_one_sync()) {...}` from
+// warp-uniform control flow compile to straight-line UTCHMMA with uniform-register operands; issued from a divergent
+// `if (lane == 0)` region the compiler wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, which was
+// measured to cost ~80 clk per MMA on the issuing warp (profiles/r02_ru_trace_a.txt)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0, both addresses 16-B aligned)
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
