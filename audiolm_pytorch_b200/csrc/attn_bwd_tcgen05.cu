@@ -126,26 +126,30 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                  tmem_dK = tmem_base + 320;
 
   if (warp == AB_TMA_WARP) {
-    if (lane == 0 && n_iter > 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
-      tma_load_3d(sK, &tmK, kv_full, 0, k0, batch);
-      tma_load_3d(sV, &tmV, kv_full, 0, k0, batch);
+    if (n_iter > 0) {  // whole warp runs the loop; one elected lane issues (see elect_one_sync)
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
+        tma_load_3d(sK, &tmK, kv_full, 0, k0, batch);
+        tma_load_3d(sV, &tmV, kv_full, 0, k0, batch);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_iter; ++it) {
         const int head = it / q_per_head, qb = qb_min + it % q_per_head;
         mbar_wait(&qdo_empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&qdo_full[stage], 2 * AB_TILE + 2 * AB_T * 4);
-        tma_load_3d(sQ + stage * AB_TILE, &tmQ, &qdo_full[stage], head * AB_D, qb * AB_T, batch);
-        tma_load_3d(sdO + stage * AB_TILE, &tmdO, &qdo_full[stage], head * AB_D, qb * AB_T, batch);
         const size_t roff = ((size_t)batch * p.h + head) * p.n_q_pad + (size_t)qb * AB_T;
-        bulk_load_1d(sLse + stage * AB_T, p.lse + roff, AB_T * 4, &qdo_full[stage]);
-        bulk_load_1d(sDelta + stage * AB_T, p.delta + roff, AB_T * 4, &qdo_full[stage]);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&qdo_full[stage], 2 * AB_TILE + 2 * AB_T * 4);
+          tma_load_3d(sQ + stage * AB_TILE, &tmQ, &qdo_full[stage], head * AB_D, qb * AB_T, batch);
+          tma_load_3d(sdO + stage * AB_TILE, &tmdO, &qdo_full[stage], head * AB_D, qb * AB_T, batch);
+          bulk_load_1d(sLse + stage * AB_T, p.lse + roff, AB_T * 4, &qdo_full[stage]);
+          bulk_load_1d(sDelta + stage * AB_T, p.delta + roff, AB_T * 4, &qdo_full[stage]);
+        }
         if (++stage == AB_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == AB_MMA_WARP) {
-    if (lane == 0 && n_iter > 0) {
+    if (n_iter > 0) {  // whole warp runs the loop; one elected lane issues (see elect_one_sync)
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(AB_T, AB_T, false, false);
       constexpr uint32_t idesc_acc = umma_idesc_bf16_f32(AB_T, AB_D, false, true);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), pt_addr = smem_u32(sPT),
@@ -155,15 +159,17 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       uint32_t phase = 0;
       auto issue_s = [&](int st) {
         const uint32_t q_addr = smem_u32(sQ + st * AB_TILE), do_addr = smem_u32(sdO + st * AB_TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k)
-          umma_bf16_ss(tmem_ST, umma_smem_desc_sw128(k_addr + k * 32, 1024, 0),
-                       umma_smem_desc_sw128(q_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16_ss(tmem_ST, umma_smem_desc_sw128(k_addr + k * 32, 1024, 0),
+                         umma_smem_desc_sw128(q_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k)
-          umma_bf16_ss(tmem_dPT, umma_smem_desc_sw128(v_addr + k * 32, 1024, 0),
-                       umma_smem_desc_sw128(do_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16_ss(tmem_dPT, umma_smem_desc_sw128(v_addr + k * 32, 1024, 0),
+                         umma_smem_desc_sw128(do_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
       };
       mbar_wait(&qdo_full[0], 0);
       tc_fence_after_sync();
@@ -183,17 +189,19 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_wait(p_full, it & 1);
         tc_fence_after_sync();
         const uint32_t q_addr = smem_u32(sQ + stage * AB_TILE), do_addr = smem_u32(sdO + stage * AB_TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
-          umma_bf16_ss(tmem_dV, umma_smem_desc_sw128(pt_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
-                       umma_smem_desc_sw128(do_addr + k * 2048, 1024, 0), idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < AB_T / 16; ++k)
+            umma_bf16_ss(tmem_dV, umma_smem_desc_sw128(pt_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
+                         umma_smem_desc_sw128(do_addr + k * 2048, 1024, 0), idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
-          umma_bf16_ss(tmem_dK, umma_smem_desc_sw128(dst_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
-                       umma_smem_desc_sw128(q_addr + k * 2048, 1024, 0), idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&qdo_empty[stage]);
-        umma_commit(pds_free);
-        if (it == n_iter - 1) umma_commit(acc_full);
+          for (int k = 0; k < AB_T / 16; ++k)
+            umma_bf16_ss(tmem_dK, umma_smem_desc_sw128(dst_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
+                         umma_smem_desc_sw128(q_addr + k * 2048, 1024, 0), idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&qdo_empty[stage]);
+          umma_commit(pds_free);
+          if (it == n_iter - 1) umma_commit(acc_full);
+        }
         stage = nstage;
         phase = nphase;
       }
@@ -389,37 +397,43 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
 
   if (warp == AB_TMA_WARP) {
-    if (lane == 0 && n_tiles > 0) {
-      mbar_arrive_expect_tx(q_full, 2 * AB_TILE);
-      tma_load_3d(sQ, &tmQ, q_full, head * AB_D, q0, batch);
-      tma_load_3d(sdO, &tmdO, q_full, head * AB_D, q0, batch);
+    if (n_tiles > 0) {  // whole warp runs the loop; one elected lane issues (see elect_one_sync)
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(q_full, 2 * AB_TILE);
+        tma_load_3d(sQ, &tmQ, q_full, head * AB_D, q0, batch);
+        tma_load_3d(sdO, &tmdO, q_full, head * AB_D, q0, batch);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * AB_TILE);
-        tma_load_3d(sK + stage * AB_TILE, &tmK, &kv_full[stage], 0, j * AB_T, batch);
-        tma_load_3d(sV + stage * AB_TILE, &tmV, &kv_full[stage], 0, j * AB_T, batch);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&kv_full[stage], 2 * AB_TILE);
+          tma_load_3d(sK + stage * AB_TILE, &tmK, &kv_full[stage], 0, j * AB_T, batch);
+          tma_load_3d(sV + stage * AB_TILE, &tmV, &kv_full[stage], 0, j * AB_T, batch);
+        }
         if (++stage == AB_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == AB_MMA_WARP) {
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0) {  // whole warp runs the loop; one elected lane issues (see elect_one_sync)
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(AB_T, AB_T, false, false);
       constexpr uint32_t idesc_acc = umma_idesc_bf16_f32(AB_T, AB_D, false, true);
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO), ds_addr = smem_u32(sdS);
       mbar_wait(q_full, 0);
       auto issue_s = [&](int st) {
         const uint32_t k_addr = smem_u32(sK + st * AB_TILE), v_addr = smem_u32(sV + st * AB_TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k)
-          umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 1024, 0),
-                       umma_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 1024, 0),
+                         umma_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < AB_D / 16; ++k)
-          umma_bf16_ss(tmem_dP, umma_smem_desc_sw128(do_addr + k * 32, 1024, 0),
-                       umma_smem_desc_sw128(v_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16_ss(tmem_dP, umma_smem_desc_sw128(do_addr + k * 32, 1024, 0),
+                         umma_smem_desc_sw128(v_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -441,13 +455,15 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_wait(p_full, j & 1);
         tc_fence_after_sync();
         const uint32_t k_addr = smem_u32(sK + stage * AB_TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
-          umma_bf16_ss(tmem_dQ, umma_smem_desc_sw128(ds_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
-                       umma_smem_desc_sw128(k_addr + k * 2048, 1024, 0), idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&kv_empty[stage]);
-        umma_commit(ds_free);
-        if (j == n_tiles - 1) umma_commit(acc_full);
+          for (int k = 0; k < AB_T / 16; ++k)
+            umma_bf16_ss(tmem_dQ, umma_smem_desc_sw128(ds_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 1024, 0),
+                         umma_smem_desc_sw128(k_addr + k * 2048, 1024, 0), idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&kv_empty[stage]);
+          umma_commit(ds_free);
+          if (j == n_tiles - 1) umma_commit(acc_full);
+        }
         stage = nstage;
         phase = nphase;
       }

@@ -102,23 +102,27 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_PV = tmem_base + ATT_BN;
 
   if (warp == ATT_TMA_WARP) {
-    if (lane == 0 && n_tiles > 0) {
-      // ---------------- TMA producer ----------------
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, q0, batch);
+    if (n_tiles > 0) {
+      // ---------------- TMA producer (whole warp runs the loop, one elected lane issues: see elect_one_sync) -------
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+        tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, q0, batch);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_3d(sK + stage * ATT_TILE_BYTES, &tmK, &kv_full[stage], 0, j * ATT_BN, batch);
-        tma_load_3d(sV + stage * ATT_TILE_BYTES, &tmV, &kv_full[stage], 0, j * ATT_BN, batch);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+          tma_load_3d(sK + stage * ATT_TILE_BYTES, &tmK, &kv_full[stage], 0, j * ATT_BN, batch);
+          tma_load_3d(sV + stage * ATT_TILE_BYTES, &tmV, &kv_full[stage], 0, j * ATT_BN, batch);
+        }
         if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == ATT_MMA_WARP) {
-    if (lane == 0 && n_tiles > 0) {
-      // ---------------- UMMA issuer ----------------
+    if (n_tiles > 0) {
+      // ---------------- UMMA issuer (whole warp, one elected lane issues) ----------------
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(ATT_BM, ATT_BN, false, false);   // Q K^T
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(ATT_BM, ATT_D, false, true);    // P V (V is MN-major)
       const uint32_t q_addr = smem_u32(sQ);
@@ -126,11 +130,13 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(q_full, 0);
       auto issue_s = [&](int stage) {
         const uint32_t k_addr = smem_u32(sK + stage * ATT_TILE_BYTES);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 1024, 0),
-                       umma_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < ATT_D / 16; ++k)
+            umma_bf16_ss(tmem_S, umma_smem_desc_sw128(q_addr + k * 32, 1024, 0),
+                         umma_smem_desc_sw128(k_addr + k * 32, 1024, 0), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -141,12 +147,14 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(p_full, j & 1);
         tc_fence_after_sync();
         const uint32_t v_addr = smem_u32(sV + stage * ATT_TILE_BYTES);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_bf16_ss(tmem_PV, umma_smem_desc_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
-                       umma_smem_desc_sw128(v_addr + k * 2048, 1024, 0), idesc_pv, k > 0 ? 1u : 0u);
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[stage]);
+          for (int k = 0; k < ATT_BN / 16; ++k)
+            umma_bf16_ss(tmem_PV, umma_smem_desc_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
+                         umma_smem_desc_sw128(v_addr + k * 2048, 1024, 0), idesc_pv, k > 0 ? 1u : 0u);
+          umma_commit(pv_full);
+          umma_commit(&kv_empty[stage]);
+        }
         if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1u; }
         if (j + 1 < n_tiles) {
           mbar_wait(&kv_full[stage], phase);

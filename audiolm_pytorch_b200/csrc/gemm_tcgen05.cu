@@ -98,8 +98,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===================== TMA producer =====================
+      // the whole warp runs the (uniform) loop; one elected lane issues.  Issuing from a divergent `if (lane == 0)` region
+      // makes the compiler wrap every UTMALDG / UTCHMMA / commit in an ELECT + BRA.U.ANY loop (see ptx_sm100.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -109,10 +111,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int m0 = mb * GEMM_BLOCK_M, n0 = nb * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
           const int k0 = kb * GEMM_BLOCK_K;
+          if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           if constexpr (!A_MN) {
             tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0, b);
           } else {
@@ -127,13 +130,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int i = 0; i < BLOCK_N / 64; ++i)
               tma_load_3d(sb + i * (GEMM_BLOCK_K * 128), &tmB, &full_bar[stage], n0 + i * 64, k0, b);
           }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== UMMA issuer =====================
+    {
+      // ===================== UMMA issuer (whole warp, one elected lane issues) =====================
       constexpr uint32_t idesc = umma_idesc_bf16_f32(GEMM_BLOCK_M, BLOCK_N, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -152,6 +156,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             const uint64_t da = A_MN ? umma_smem_desc_sw128(a_addr + k * 2048, 1024, GEMM_BLOCK_K * 128)
@@ -162,6 +167,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (kb == kb1 - 1) umma_commit(&acc_full_bar[acc]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
