@@ -24,6 +24,7 @@ SIGNATURES: dict[str, list] = {
     "alm_gemm_bf16": [P, I, L, L, P, I, L, L, P, I, L, L, I, I, I, I, F, P, I, I, P],
     "alm_mqa_attn_fwd": [P, L, P, L, L, P, L, L, P, P, L, P, L, P, L, L, I, I, I, I, I, F, P],
     "alm_mqa_attn_bwd": [P, L, P, L, L, P, L, L, P, L, P, P, P, I, P, L, P, L, P, L, P, P, L, L, I, I, I, I, I, F, P],
+    "alm_pack_key_mask": [P, P, I, I, P],
     "alm_attn_delta": [P, L, P, L, P, L, I, I, I, P],
     "alm_kv_append": [P, L, P, P, L, P, I, I, P],
     "alm_gemv_bf16": [P, L, P, L, P, I, L, P, I, I, I, P],

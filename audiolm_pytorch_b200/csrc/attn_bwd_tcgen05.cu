@@ -26,7 +26,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct AttnBwdParams {
   const float* lse;      // [b, h, n_q_pad]  log2-domain LSE (m + log2 l) as written by the forward
   const float* delta;    // [b, h, n_q_pad]
-  const uint8_t* kmask;  // [b, n_k] or null
+  const uint32_t* kmask;  // packed key mask bits (alm_pack_key_mask) or null
+  int kb_stride;          // words per batch row
   const float* bias;     // [h, n_q, bias_rs] additive score bias (as given to the forward) or null
   float* dbias;          // same layout, fp32: d(bias) is ACCUMULATED (red.add) over batches / calls; or null
   long long bias_hs, bias_rs;
@@ -214,7 +215,7 @@ mqa_attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int kj = k0 + row;
     const uint32_t lane_sel = uint32_t(quad * 32) << 16;
     bool key_ok = kj < p.n_k;
-    if (key_ok && p.kmask != nullptr) key_ok = p.kmask[(size_t)batch * p.n_k + kj] != 0;
+    if (key_ok && p.kmask != nullptr) key_ok = (p.kmask[(size_t)batch * p.kb_stride + (kj >> 5)] >> (kj & 31)) & 1u;
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < n_iter; ++it) {
@@ -477,7 +478,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float lse = p.lse[roff];          // log2-domain; n_q_pad >= n_qblocks*128: always in bounds
     const float delta = p.delta[roff];
     const int q_limit = p.causal ? qi + off : p.n_k - 1;
-    const uint8_t* mrow = p.kmask ? p.kmask + (size_t)batch * p.n_k : nullptr;
+    const uint32_t* mrow = p.kmask ? p.kmask + (size_t)batch * p.kb_stride : nullptr;
     [[maybe_unused]] const float* brow =
         HAS_BIAS ? p.bias + (long long)head * p.bias_hs + (long long)min(qi, p.n_q - 1) * p.bias_rs : nullptr;
     for (int j = 0; j < n_tiles; ++j) {
@@ -488,6 +489,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                              (!p.causal || kbase + AB_T - 1 <= q0 + off);
       {
         const int c = part;
+        const uint32_t mbits = mrow != nullptr ? __ldg(mrow + j * 4 + c) : 0xFFFFFFFFu;  // this warp's 32 keys
         uint32_t rs[32], rp[32];
         __syncwarp();
         tmem_ld_32x32b_x32(tmem_S + lane_sel + c * 32, rs);
@@ -529,7 +531,7 @@ mqa_attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             bool ok = tile_full;
             if (!tile_full) {
               ok = qi < p.n_q && kj < p.n_k && kj <= q_limit;
-              if (ok && mrow != nullptr) ok = mrow[kj] != 0;
+              ok = ok && ((mbits >> (g * 8 + e)) & 1u);
             }
             const float s = __uint_as_float(rs[g * 8 + e]);
             float shift = -lse;
@@ -627,7 +629,8 @@ extern "C" int alm_mqa_attn_bwd(const void* q, int64_t ldq, const void* k, int64
   }
   AttnBwdParams p;
   p.lse = lse; p.delta = delta;
-  p.kmask = reinterpret_cast<const uint8_t*>(key_mask);
+  p.kmask = reinterpret_cast<const uint32_t*>(key_mask);
+  p.kb_stride = (n_k + 127) / 128 * 4;
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.bias = bias; p.dbias = dbias; p.bias_hs = bias_hstride; p.bias_rs = bias_rstride;

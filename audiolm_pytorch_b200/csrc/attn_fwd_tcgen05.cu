@@ -29,7 +29,8 @@ constexpr int ATT_TMEM_COLS = 256;
 struct AttnFwdParams {
   __nv_bfloat16* o;       // [b, n_q, h*64] row stride ldo
   float* lse;             // [b, h, lse_stride] log2-domain LSE of the scaled scores (for backward); may be null
-  const uint8_t* kmask;   // [b, n_k] 1 = attend, 0 = masked; may be null
+  const uint32_t* kmask;  // packed key mask (alm_pack_key_mask): bit i of word w of row b = key 32 w + i may be attended; may be null
+  int kb_stride;          // words per batch row: 4 * ceil(n_k / 128)
   const float* bias;      // [h, n_q, bias_rs] additive score bias (natural-log domain, added after the scale); may be null
   long long bias_hs, bias_rs;  // element strides between heads / query rows (bias_rs % 4 == 0, >= n_k)
   long long ldo, lse_stride;
@@ -177,7 +178,7 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int d = 0; d < 32; ++d) o_acc[d] = 0.f;
     const int q_limit = p.causal ? qi + off : p.n_k - 1;  // last key index this query may see
-    const uint8_t* mrow = p.kmask ? p.kmask + (long long)batch * p.n_k : nullptr;
+    const uint32_t* mrow = p.kmask ? p.kmask + (long long)batch * p.kb_stride : nullptr;
     uint8_t* ptile = sP + half * ATT_TILE_BYTES;
 
     auto add_pv = [&](float a) {
@@ -212,29 +213,9 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // key validity bits of the whole 128-key tile (the row max needs all of it)
       uint32_t valid[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
       if (!tile_full) {
-        if (mrow != nullptr) {
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            uint32_t bits = 0;
-#pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-              const int kk = kbase + w * 32 + q4 * 16;
-              uint4 mv = make_uint4(0, 0, 0, 0);
-              if (kk + 16 <= p.n_k && ((reinterpret_cast<uintptr_t>(mrow + kk) & 15u) == 0)) {
-                mv = __ldg(reinterpret_cast<const uint4*>(mrow + kk));
-              } else {
-                uint8_t tmp[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) tmp[e] = (kk + e < p.n_k) ? __ldg(mrow + kk + e) : 0;
-                mv = *reinterpret_cast<uint4*>(tmp);
-              }
-              const uint32_t words[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if ((words[e >> 2] >> ((e & 3) * 8)) & 0xFFu) bits |= 1u << (q4 * 16 + e);
-            }
-            valid[w] = bits;
-          }
+        if (mrow != nullptr) {  // one 16-B load: the 128 key bits of this tile (shared by every row of the CTA)
+          const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mrow + j * 4));
+          valid[0] = mv.x; valid[1] = mv.y; valid[2] = mv.z; valid[3] = mv.w;
         }
         const int lim = min(q_limit, p.n_k - 1) - kbase;  // keys 0..lim of this tile are in range
 #pragma unroll
@@ -377,6 +358,32 @@ mqa_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 }  // namespace alm
 
+namespace alm {
+// key mask bytes [b, n_k] (non-zero = attend) -> bits [b, 4 * ceil(n_k / 128)] (keys past n_k: 0)
+__global__ void pack_key_mask_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits, int n_k, int words) {
+  const int b = blockIdx.y;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= words) return;
+  const int k = w * 32 + (threadIdx.x & 31);
+  const bool on = k < n_k && mask[(long long)b * n_k + k] != 0;
+  const uint32_t v = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0) bits[(long long)b * words + w] = v;
+}
+}  // namespace alm
+
+extern "C" int alm_pack_key_mask(const void* key_mask, void* bits, int b, int n_k, alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(key_mask && bits && b > 0 && n_k > 0, ALM_ERR_ARG);
+  const int words = (n_k + 127) / 128 * 4;
+  dim3 grid(ceil_div(words, 8), b);
+  pack_key_mask_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(key_mask),
+                                                 reinterpret_cast<uint32_t*>(bits), n_k, words);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
 extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, int64_t k_bstride,
                                 const void* v, int64_t ldv, int64_t v_bstride, const void* key_mask, void* o,
                                 int64_t ldo, float* lse, int64_t lse_stride, const float* bias, int64_t bias_hstride,
@@ -416,7 +423,8 @@ extern "C" int alm_mqa_attn_fwd(const void* q, int64_t ldq, const void* k, int64
   AttnFwdParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.lse = lse;
-  p.kmask = reinterpret_cast<const uint8_t*>(key_mask);
+  p.kmask = reinterpret_cast<const uint32_t*>(key_mask);
+  p.kb_stride = (n_k + 127) / 128 * 4;
   p.bias = bias;
   p.bias_hs = bias_hstride;
   p.bias_rs = bias_rstride;

@@ -119,6 +119,26 @@ def _check_bias(bias, heads, n_q, n_k):
     return bias.stride(0), bias.stride(1)
 
 
+class PackedKeyMask:
+    """key mask in the bit layout the attention kernels read (alm_pack_key_mask): uint32 [b, 4 * ceil(n_k / 128)]"""
+
+    def __init__(self, bits, n_k):
+        self.bits, self.n_k = bits, n_k
+
+
+def pack_key_mask(key_mask):
+    """bool / uint8 [b, n_k] (True = attend) -> PackedKeyMask; pack once per forward and hand the result to every
+    layer's mqa_attn_fwd / mqa_attn_bwd."""
+    if key_mask is None or isinstance(key_mask, PackedKeyMask):
+        return key_mask
+    _check_cuda(key_mask)
+    m = key_mask.to(torch.uint8).contiguous()
+    b, n_k = m.shape
+    bits = torch.empty(b, (n_k + 127) // 128 * 4, device=m.device, dtype=torch.int32)
+    _lib.call("alm_pack_key_mask", m, bits, b, n_k)
+    return PackedKeyMask(bits, n_k)
+
+
 def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, return_lse=True, bias=None):
     """Multi-query attention forward (attend.py:69-146).
 
@@ -128,7 +148,7 @@ def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, retu
     bias: optional fp32 [heads, n_q, >=n_k] additive score bias shared by the batch (attend.py:122-124).
     Returns o [b, n_q, heads*64] bf16 and lse [b, heads, n_q] fp32.
     """
-    _check_cuda(q, k, v, key_mask, bias)
+    _check_cuda(q, k, v, bias)
     assert q.dtype == bf16 and k.dtype == bf16 and v.dtype == bf16
     b, n_q, hd = q.shape
     n_k = k.shape[1]
@@ -138,9 +158,10 @@ def mqa_attn_fwd(q, k, v, *, heads, key_mask=None, causal=True, scale=None, retu
     o = torch.empty(b, n_q, hd, device=q.device, dtype=bf16)
     n_q_pad = (n_q + 127) // 128 * 128  # the backward stages lse rows with 512-B bulk copies
     lse = torch.empty(b, heads, n_q_pad, device=q.device, dtype=f32) if return_lse else None
+    key_mask = pack_key_mask(key_mask)
     if key_mask is not None:
-        key_mask = key_mask.to(torch.uint8).contiguous()
-        assert key_mask.shape == (b, n_k)
+        assert key_mask.n_k == n_k and key_mask.bits.shape[0] == b
+        key_mask = key_mask.bits
     if scale is None:
         scale = 64 ** -0.5
     # algorithmic FLOPs: QK^T + PV over the visible (lower-triangle) part only
@@ -161,7 +182,7 @@ def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, sca
     lse is the padded [b, heads, n_q_pad] tensor returned by the forward.  With a bias, d(bias) is ACCUMULATED
     into `dbias` (fp32, same shape/strides as `bias`; the caller zeroes it once per step).
     """
-    _check_cuda(q, k, v, o, d_o, lse, key_mask, bias, dbias)
+    _check_cuda(q, k, v, o, d_o, lse, bias, dbias)
     b, n_q, hd = q.shape
     n_k = k.shape[1]
     n_q_pad = lse.shape[-1]
@@ -169,8 +190,10 @@ def mqa_attn_bwd(q, k, v, o, d_o, lse, *, heads, key_mask=None, causal=True, sca
     assert d_o.stride(0) == n_q * d_o.stride(1)
     delta = torch.empty(b, heads, n_q_pad, device=q.device, dtype=f32)
     _lib.call("alm_attn_delta", o, o.stride(1), d_o, d_o.stride(1), delta, n_q_pad, b, heads, n_q)
+    key_mask = pack_key_mask(key_mask)
     if key_mask is not None:
-        key_mask = key_mask.to(torch.uint8).contiguous()
+        assert key_mask.n_k == n_k
+        key_mask = key_mask.bits
     if scale is None:
         scale = 64 ** -0.5
     dq = torch.empty(b, n_q, hd, device=q.device, dtype=bf16)

@@ -378,7 +378,7 @@ class Transformer(nn.Module):
         M = b * n
         H = self.heads
         x2 = x.detach().reshape(M, d).to(f32).contiguous()
-        mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        mask_u8 = ops.pack_key_mask(mask)  # bits, packed once for every layer and the backward
         L = []
         hc0 = self.layers[0][0]
         R, bin_, xn, beta, aux = ops.hc_pre_fwd(hc0.kernel_params(), hc0.branch.norm.gamma, x_expand=x2, M=M, d=d)
@@ -535,7 +535,7 @@ class Transformer(nn.Module):
         M = b * n
         r = x.detach().reshape(M, d).to(f32).contiguous()
         x2 = r
-        mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        mask_u8 = ops.pack_key_mask(mask)  # bits, packed once for every layer and the backward
         L, kvs = [], []
         a0 = self.layers[0][0].branch
         r, xn, raw, st = ops.resid_ln_fwd(r, None, a0.norm.gamma, want_raw=True)
@@ -630,7 +630,7 @@ class Transformer(nn.Module):
         M = b * n
         H = self.heads
         x2 = x.reshape(M, d).to(f32).contiguous()
-        mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        mask_u8 = ops.pack_key_mask(mask)  # bits, packed once for every layer and the backward
         hc0 = self.layers[0][0]
         R, bin_, xn, beta, _ = ops.hc_pre_fwd(hc0.kernel_params(), hc0.branch.norm.gamma, x_expand=x2, M=M, d=d)
         v_first = None

@@ -57,8 +57,14 @@ int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const v
 
 /* ---- multi-query attention (tcgen05 + TMA, flash-style online softmax) ----------------------- */
 /*
+ * Key-padding / forgetful-causal mask in the form the attention kernels read: uint8 [b, n_k] (non-zero = attend) ->
+ * uint32 bits [b, 4 * ceil(n_k / 128)], bit i of word w = key 32 w + i.  One call per forward (all layers and the
+ * backward share the result); a 128-key tile then costs every CTA one 16-byte load instead of 128 byte tests per row.
+ */
+int alm_pack_key_mask(const void* key_mask, void* bits, int b, int n_k, alm_stream_t stream);
+/*
  * o[b,i,h*64:(h+1)*64] = softmax_j( q[b,i,h,:]·k[b,j,:] * scale, masked ) · v[b,j,:]
- *   one shared k/v head of width 64 (MQA); key_mask[b,j] (uint8, 1 = attend) optional;
+ *   one shared k/v head of width 64 (MQA); key_mask: PACKED bits from alm_pack_key_mask (attend = 1), optional;
  *   causal: query i sees keys j <= i + (n_k - n_q) (right-aligned, as needed by the KV cache).
  *   lse[b,h,i] (optional, row stride lse_stride >= n_q) = log2-domain log-sum-exp (log2 sum_j 2^(s_ij*scale*log2e)) of the masked scores for the backward.
  * Replaces Attend.forward / flash_attn (attend.py:69-146) as called by Attention.forward
