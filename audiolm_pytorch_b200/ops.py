@@ -636,6 +636,14 @@ def rvq_encode_tc(x, packed_codebooks):
     return quant, idx
 
 
+def nearest_centroid(x, packed_centroids):
+    """cluster assignment of HubertWithKmeans.forward (hubert_kmeans.py:114-116: `(-torch.cdist(embed, centers)).argmax(-1)`):
+    x [N, D] fp32, packed_centroids = rvq_pack_codebooks(centers[None]) -> ids [N] int64.  Same kernels as one RVQ stage:
+    the distance GEMM on the tensor cores, then the exact fp32 re-rank (lowest index on ties, as argmax does)."""
+    _, idx = rvq_encode_tc(x, packed_centroids)
+    return idx[:, 0]
+
+
 def rvq_decode(indices, codebooks):
     """indices [N, Q] int64 (-1 = dropped) -> sum of selected codes [N, D] fp32."""
     _check_cuda(indices, codebooks)

@@ -3,8 +3,8 @@
 Drop-in surface of /root/reference/audiolm_pytorch/soundstream.py:314-395, 451-866 for the calls the AudioLM
 hot path makes: `forward(x, return_encoded=True | return_codes_only=True | return_recons_only=True)`,
 `tokenize`, `decode_from_codebook_indices`, `decode`, with the reference's constructor kwargs and
-state_dict keys for `encoder.*`, `decoder.*`, `rq.*`.  GAN / mel training losses, the local-attention
-bottleneck (use_local_attn=True), LFQ / FSQ quantizers and FiLM denoising are outside this build.
+state_dict keys for `encoder.*`, `decoder.*`, `rq.*`.  GAN / mel training losses, LFQ / FSQ quantizers and
+FiLM denoising are outside this build; the local-attention bottleneck lives in local_attn.py.
 """
 from __future__ import annotations
 
@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .local_attn import LocalTransformer
 
 f32 = torch.float32
 
@@ -202,9 +203,6 @@ class SoundStream(nn.Module):
         cfg.pop("self", None)
         cfg.pop("__class__", None)
         self._configs = pickle.dumps(cfg)
-        if use_local_attn:
-            raise NotImplementedError("the LocalMHA bottleneck (use_local_attn=True) is not built yet; "
-                                      "construct with use_local_attn=False")
         if use_lookup_free_quantizer or use_finite_scalar_quantizer or use_gate_loop_layers:
             raise NotImplementedError("LFQ / FSQ / gate-loop variants are outside this build")
         assert exists(codebook_size)
@@ -217,8 +215,12 @@ class SoundStream(nn.Module):
             CausalConv1d(input_channels, channels, 7, pad_mode=pad_mode),
             *[EncoderBlock(ci, co, s, enc_cycle_dilations, squeeze_excite, pad_mode) for (ci, co), s in zip(pairs, strides)],
             CausalConv1d(layer_channels[-1], codebook_dim, 3, pad_mode=pad_mode))
-        self.encoder_attn = None
-        self.decoder_attn = None
+        attn_kwargs = dict(dim=codebook_dim, dim_head=attn_dim_head, heads=attn_heads, depth=attn_depth,
+                           window_size=attn_window_size, xpos_scale_base=attn_xpos_scale_base,
+                           dynamic_pos_bias=attn_dynamic_pos_bias, prenorm=True, causal=True)
+        # windowed causal attention bottleneck on both sides of the quantizer (soundstream.py:533-545, 613)
+        self.encoder_attn = LocalTransformer(**attn_kwargs) if use_local_attn else None
+        self.decoder_attn = LocalTransformer(**attn_kwargs) if use_local_attn else None
         self.num_quantizers = rq_num_quantizers
         self.codebook_dim = codebook_dim
         self.codebook_size = codebook_size
@@ -278,7 +280,7 @@ class SoundStream(nn.Module):
     def _tc_plan(self):
         """layer list for the split-bf16 tensor-core encoder, or None when this configuration is outside what those
         kernels are built for (then the fp32 CUDA-core kernels run).  Structure follows soundstream.py:519-531."""
-        if not (ENCODER_ON_TENSOR_CORES and self.single_channel and self.encoder_attn is None):
+        if not (ENCODER_ON_TENSOR_CORES and self.single_channel):
             return None
         enc = list(self.encoder)
         first, blocks, last = enc[0], enc[1:-1], enc[-1]
@@ -362,6 +364,8 @@ class SoundStream(nn.Module):
     def decode(self, x, quantize=False):
         if quantize:
             x, *_ = self.rq(x)
+        if exists(self.decoder_attn):
+            x = self.decoder_attn(x)
         return self.decoder(x.transpose(1, 2).contiguous())
 
     @torch.no_grad()
@@ -376,12 +380,16 @@ class SoundStream(nn.Module):
             raise NotImplementedError("FiLM denoising / target losses are outside this build")
         x, lead = self.process_input(x, input_sample_hz=input_sample_hz, curtail_from_left=curtail_from_left)
         h = self.encode_frames(x)                                      # b n c
+        if exists(self.encoder_attn):
+            h = self.encoder_attn(h)
         quantized, indices, commit_loss = self.rq(h)
         if return_codes_only:
             return indices
         if return_encoded:
             g, b, n, q = indices.shape
             return quantized, indices.permute(1, 2, 0, 3).reshape(b, n, g * q), commit_loss
+        if exists(self.decoder_attn):
+            quantized = self.decoder_attn(quantized)
         recon = self.decoder(quantized.transpose(1, 2).contiguous())
         if return_recons_only:
             return recon.reshape(*lead, *recon.shape[-2:]) if len(lead) != 1 else recon

@@ -224,6 +224,20 @@ def codec_bench(dev, clips=32, iters=5):
         ops.profile_start()
         ss(wave, return_encoded=True)
         prof = ops.profile_stop()
+    # the constructor's default configuration: LocalTransformer bottleneck (use_local_attn=True) before the quantizer
+    try:
+        torch.manual_seed(7)
+        ssd = SoundStream(codebook_size=1024, rq_num_quantizers=8, target_sample_hz=24000)
+        for rvq in ssd.rq.rvqs:
+            for layer in rvq.layers:
+                layer._codebook.embed.normal_()
+                layer._codebook.initted.fill_(True)
+        ssd = ssd.to(dev).eval()
+        with torch.no_grad():
+            ms_default = _timed_cuda(lambda: ssd(wave, return_encoded=True), iters)
+        del ssd
+    except Exception as e:  # pragma: no cover
+        ms_default = None
     frames = clips * 150
     kern = {cls: {"ms_per_call": ms_, "launches": n_,
                   ("gbps" if ops.CLASS_UNIT.get(cls) == "byte" else "tflops"): work / (ms_ * 1e-3) / (1e9 if ops.CLASS_UNIT.get(cls) == "byte" else 1e12) if ms_ else 0.0}
@@ -234,7 +248,11 @@ def codec_bench(dev, clips=32, iters=5):
             "ms_per_call": ms, "clips": clips, "samples_per_clip": 48000, "kernels": kern,
             "encoder_convs": {"ms": conv_ms, "algorithmic_gbps": enc_gbps, "frac_of_hbm_peak": enc_gbps / pk["hbm"],
                               "algorithmic_bytes": ENC_BYTES_PER_CLIP * clips},
-            "decode": {"frames_per_s": frames / (ms_dec * 1e-3), "ms_per_call": ms_dec}}
+            "decode": {"frames_per_s": frames / (ms_dec * 1e-3), "ms_per_call": ms_dec},
+            "default_ctor_with_local_attn": None if ms_default is None else
+            {"frames_per_s": frames / (ms_default * 1e-3), "ms_per_call": ms_default},
+            "config": "use_local_attn=False (the kernels the north star names); default_ctor_with_local_attn adds the "
+                      "LocalTransformer bottleneck"}
 
 
 # ------------------------------------------------------------------------------------------------

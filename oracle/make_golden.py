@@ -525,12 +525,41 @@ def golden_soundstream(ref):
                     convs=convs), GOLDEN / "soundstream.pt")
 
 
+def golden_local_attn(ref):
+    """SoundStream with its default bottleneck (use_local_attn=True, soundstream.py:397-440, 545, 613, 832-833, 857-858):
+    the reference's LocalTransformer over the restated local-attention package (oracle/third_party.py, PARITY UNPINNED
+    upstream).  Small sizes: window 8, 30 frames -> 4 buckets with a ragged last one."""
+    torch.manual_seed(91)
+    kw = dict(codebook_size=64, rq_num_quantizers=4, channels=4, codebook_dim=32, attn_window_size=8,
+              target_sample_hz=24000)
+    ss = ref.ss.SoundStream(**kw).eval()
+    tp.seed_codebooks(ss.rq, seed=7, std=0.5)
+    g = torch.Generator().manual_seed(92)
+    with torch.no_grad():
+        for n_, p_ in ss.named_parameters():   # move the attention block off its init (gates, scales, norms)
+            if "_attn." in n_ and p_.ndim == 1:
+                p_.add_(torch.randn(p_.shape, generator=g) * 0.1)
+    wave = torch.randn(2, 9600)
+    h = torch.randn(2, 30, 32)
+    with torch.no_grad():
+        enc_attn_out = ss.encoder_attn(h)
+        quant, idx, _ = ss(wave, return_encoded=True)
+        recon = ss(wave, return_recons_only=True)
+        recon_idx = ss.decode_from_codebook_indices(idx)
+    st = {k: v for k, v in clone_state(ss).items()
+          if k.split(".")[0] in ("encoder", "decoder", "rq", "encoder_attn", "decoder_attn")}
+    print("local attention bottleneck:")
+    check("round trip with decoder_attn (README.md:100-113)", recon_idx, recon, tol=1e-5)
+    torch.save(dict(kwargs=kw, state=st, wave=wave, h=h, enc_attn_out=enc_attn_out, quant=quant, idx=idx, recon=recon),
+               GOLDEN / "local_attn.pt")
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     import random
     ref = ref_import.load()
     fns = (golden_attend, golden_semantic, golden_semantic_plain, golden_coarse, golden_fine, golden_relpos,
-           golden_wrappers, golden_sampling, golden_soundstream)
+           golden_wrappers, golden_sampling, golden_soundstream, golden_local_attn)
     only = set(sys.argv[1:])
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

@@ -56,8 +56,8 @@ def load():
     _stub("encodec.utils", _linear_overlap_add=None)
     _stub("vector_quantize_pytorch", GroupedResidualVQ=tp.GroupedResidualVQ, GroupedResidualLFQ=_Absent,
           GroupedResidualFSQ=_Absent, ResidualVQ=tp.ResidualVQ)
-    _stub("local_attention", LocalMHA=_Absent)
-    _stub("local_attention.transformer", FeedForward=_Absent, DynamicPositionBias=_Absent)
+    _stub("local_attention", LocalMHA=tp.LocalMHA)
+    _stub("local_attention.transformer", FeedForward=tp.LocalFeedForward, DynamicPositionBias=_Absent)
     _stub("gateloop_transformer", SimpleGateLoopLayer=_Absent)
     _stub("hyper_connections",
           get_init_and_expand_reduce_stream_functions=tp.get_init_and_expand_reduce_stream_functions)

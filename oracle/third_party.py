@@ -201,3 +201,156 @@ def seed_codebooks(rq: GroupedResidualVQ, seed=7, std=1.0):
             cb.embed.copy_(torch.randn(cb.embed.shape, generator=g) * std)
             cb.embed_avg.copy_(cb.embed)
             cb.initted.fill_(True)
+
+
+# ----------------------------------------------------------------------------------------------
+# local-attention (>= 1.9.0): LocalMHA / LocalAttention / SinusoidalEmbeddings (xpos) / FeedForward
+# PARITY UNPINNED: the package is declared in /root/reference/setup.py:32 but its source is absent offline.  Restated
+# from the published implementation with the constructor kwargs the reference passes (soundstream.py:414-428, 533-543:
+# causal, prenorm, qk_rmsnorm, use_xpos, use_rotary_pos_emb, gate_values_per_head, window_size, xpos_scale_base) and the
+# upstream state_dict keys (norm.*, to_qkv.weight, q_scale, k_scale, to_v_gate.0.*, to_out.weight,
+# attn_fn.rel_pos.inv_freq).  Eval path only (dropout 0).
+# ----------------------------------------------------------------------------------------------
+def _l2norm(t):
+    return F.normalize(t, dim=-1)
+
+
+def _look_around(x, backward=1, forward=0, pad_value=-1, dim=2):
+    """concat each window with its `backward` predecessors / `forward` successors along `dim` (windows at dim 1)."""
+    t = x.shape[1]
+    dims = (len(x.shape) - dim) * (0, 0)
+    padded = F.pad(x, (*dims, backward, forward), value=pad_value)
+    return torch.cat([padded[:, ind:(ind + t), ...] for ind in range(forward + backward + 1)], dim=dim)
+
+
+class SinusoidalEmbeddings(nn.Module):
+    def __init__(self, dim, scale_base=None, use_xpos=False, theta=10000):
+        super().__init__()
+        self.register_buffer("inv_freq", 1.0 / (theta ** (torch.arange(0, dim, 2).float() / dim)))
+        self.use_xpos = use_xpos
+        self.scale_base = scale_base
+        assert not (use_xpos and scale_base is None)
+        self.register_buffer("scale", (torch.arange(0, dim, 2) + 0.4 * dim) / (1.4 * dim), persistent=False)
+
+    def forward(self, x):
+        seq_len = x.shape[-2]
+        t = torch.arange(seq_len, device=x.device).type_as(self.inv_freq)
+        freqs = torch.einsum("i,j->ij", t, self.inv_freq)
+        freqs = torch.cat((freqs, freqs), dim=-1)
+        if not self.use_xpos:
+            return freqs, torch.ones(1, device=x.device)
+        power = (t - (seq_len // 2)) / self.scale_base
+        scale = self.scale ** power[:, None]
+        return freqs, torch.cat((scale, scale), dim=-1)
+
+
+def _rotate_half(x):
+    x1, x2 = x.reshape(*x.shape[:-1], 2, x.shape[-1] // 2).unbind(dim=-2)
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def _apply_rotary(q, k, freqs, scale=1):
+    q_len = q.shape[-2]
+    q_freqs = freqs[..., -q_len:, :]
+    inv_scale = scale ** -1
+    if torch.is_tensor(scale) and scale.ndim == 2:
+        scale = scale[-q_len:, :]
+    q = (q * q_freqs.cos() * scale) + (_rotate_half(q) * q_freqs.sin() * scale)
+    k = (k * freqs.cos() * inv_scale) + (_rotate_half(k) * freqs.sin() * inv_scale)
+    return q, k
+
+
+class LocalAttention(nn.Module):
+    def __init__(self, *, dim, window_size, causal=False, look_backward=1, look_forward=None, autopad=False,
+                 exact_windowsize=False, scale=None, use_rotary_pos_emb=True, use_xpos=False, xpos_scale_base=None,
+                 **_):
+        super().__init__()
+        look_forward = (0 if causal else 1) if look_forward is None else look_forward
+        assert not (causal and look_forward > 0)
+        self.scale, self.window_size, self.causal = scale, window_size, causal
+        self.autopad, self.exact_windowsize = autopad, exact_windowsize
+        self.look_backward, self.look_forward = look_backward, look_forward
+        self.rel_pos = None
+        if use_rotary_pos_emb:
+            self.rel_pos = SinusoidalEmbeddings(dim, use_xpos=use_xpos,
+                                                scale_base=window_size // 2 if xpos_scale_base is None else xpos_scale_base)
+
+    def forward(self, q, k, v, mask=None, attn_bias=None):
+        assert mask is None and attn_bias is None, "restated for the reference's call (no mask, no dynamic bias)"
+        lead = q.shape[:-2]
+        q, k, v = (t.reshape(-1, *t.shape[-2:]) for t in (q, k, v))
+        ws = self.window_size
+        orig_n = q.shape[1]
+        if self.autopad:
+            pad = (-orig_n) % ws
+            q, k, v = (F.pad(t, (0, 0, 0, pad)) for t in (q, k, v))
+        b, n, dh = q.shape
+        scale = dh ** -0.5 if self.scale is None else self.scale
+        windows = n // ws
+        b_t = torch.arange(n, device=q.device).reshape(1, windows, ws)
+        bq, bk, bv = (t.reshape(b, windows, ws, dh) for t in (q, k, v))
+        bq = bq * scale
+        la = dict(backward=self.look_backward, forward=self.look_forward, pad_value=-1)
+        bk, bv = _look_around(bk, **la), _look_around(bv, **la)
+        if self.rel_pos is not None:
+            pos_emb, xpos_scale = self.rel_pos(bk)
+            bq, bk = _apply_rotary(bq, bk, pos_emb, scale=xpos_scale)
+        bq_t = b_t[..., :, None]
+        bq_k = _look_around(b_t, **la)[..., None, :]
+        pad_mask = bq_k == -1
+        sim = torch.einsum("bhie,bhje->bhij", bq, bk)
+        neg = -torch.finfo(sim.dtype).max
+        if self.causal:
+            causal_mask = bq_t < bq_k
+            if self.exact_windowsize:
+                causal_mask = causal_mask | (bq_t > (bq_k + ws * self.look_backward))
+            sim = sim.masked_fill(causal_mask, neg)
+        sim = sim.masked_fill(pad_mask, neg)
+        attn = sim.softmax(dim=-1)
+        out = torch.einsum("bhij,bhje->bhie", attn, bv).reshape(b, n, dh)
+        return out[:, :orig_n].reshape(*lead, orig_n, dh)
+
+
+class LocalMHA(nn.Module):
+    def __init__(self, *, dim, window_size, dim_head=64, heads=8, dropout=0.0, causal=False, prenorm=False,
+                 qk_rmsnorm=False, qk_scale=8, use_xpos=False, xpos_scale_base=None, exact_windowsize=None,
+                 gate_values_per_head=False, **kwargs):
+        super().__init__()
+        inner = dim_head * heads
+        self.norm = nn.LayerNorm(dim) if prenorm else None
+        self.heads = heads
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.qk_rmsnorm = qk_rmsnorm
+        if qk_rmsnorm:
+            self.q_scale = nn.Parameter(torch.ones(dim_head))
+            self.k_scale = nn.Parameter(torch.ones(dim_head))
+        self.attn_fn = LocalAttention(dim=dim_head, window_size=window_size, causal=causal, autopad=True,
+                                      scale=(qk_scale if qk_rmsnorm else None),
+                                      exact_windowsize=True if exact_windowsize is None else exact_windowsize,
+                                      use_xpos=use_xpos, xpos_scale_base=xpos_scale_base, **kwargs)
+        self.to_v_gate = nn.Sequential(nn.Linear(dim, heads)) if gate_values_per_head else None
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+    def forward(self, x, mask=None, attn_bias=None):
+        if self.norm is not None:
+            x = self.norm(x)
+        b, n, _ = x.shape
+        q, k, v = (t.reshape(b, n, self.heads, -1).transpose(1, 2) for t in self.to_qkv(x).chunk(3, dim=-1))
+        if self.qk_rmsnorm:
+            q, k = _l2norm(q) * self.q_scale, _l2norm(k) * self.k_scale
+        out = self.attn_fn(q, k, v, mask=mask, attn_bias=attn_bias)
+        if self.to_v_gate is not None:
+            out = out * self.to_v_gate(x).transpose(1, 2)[..., None].sigmoid()
+        return self.to_out(out.transpose(1, 2).reshape(b, n, -1))
+
+
+class _GEGLU(nn.Module):
+    def forward(self, x):
+        x, gate = x.chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+def LocalFeedForward(dim, mult=4, dropout=0.0):
+    inner = int(dim * mult * 2 / 3)
+    return nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, inner * 2, bias=False), _GEGLU(), nn.Dropout(dropout),
+                         nn.Linear(inner, dim, bias=False))

@@ -275,3 +275,18 @@ def test_conv_tc_vs_oracle(cin, cout, k, s, T, mode):
     assert err(ops.c8s_unpack(y), ref) < 1e-4 * scale
     y32 = ops.codec_conv_tc(xc, wu, b.to(DEV), cout=cout, kernel_size=k, stride=s, pad_mode=mode, out_fp32=True)
     assert err(y32.transpose(1, 2), ref) < 1e-4 * scale
+
+
+def test_kmeans_nearest_centroid_vs_cdist():
+    """HubertWithKmeans cluster assignment (hubert_kmeans.py:114-116) at HuBERT-base sizes: 768-d features, 500 clusters"""
+    from audiolm_pytorch_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    centers = torch.randn(500, 768, generator=g)
+    x = torch.randn(3000, 768, generator=g) * 1.5
+    d = torch.cdist(x.double(), centers.double())
+    ref = (-d).argmax(dim=-1)
+    top2 = d.topk(2, dim=-1, largest=False).values
+    safe = (top2[:, 1] - top2[:, 0]) > 1e-4
+    ids = ops.nearest_centroid(x.to(DEV), ops.rvq_pack_codebooks(centers[None].to(DEV))).cpu()
+    assert safe.float().mean() > 0.99 and torch.equal(ids[safe], ref[safe])
