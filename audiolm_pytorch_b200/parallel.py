@@ -69,11 +69,18 @@ class FlatGradBucket:
             return None
         world = dist.get_world_size(group)
         self.sync_views()
+        if self._has_avg(group) and not async_op:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)  # ncclAvg: no separate 1/world pass
+            return None
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if async_op:
             return work
         self.flat.div_(world)
         return None
+
+    @staticmethod
+    def _has_avg(group=None):
+        return dist.get_backend(group) == "nccl"
 
     # ---- overlapped exchange ----------------------------------------------------------------------
     def range_of(self, params):
@@ -88,7 +95,8 @@ class FlatGradBucket:
         """start the SUM all-reduce of flat[lo:hi]; the 1/world scale is applied by finish()."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1 or hi <= lo:
             return
-        self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+        op = dist.ReduceOp.AVG if self._has_avg(group) else dist.ReduceOp.SUM
+        self._pending.append(dist.all_reduce(self.flat[lo:hi], op=op, group=group, async_op=True))
         self._done.append((lo, hi))
 
     def finish(self, group=None):
@@ -98,16 +106,18 @@ class FlatGradBucket:
             return
         if not self._done:
             self.sync_views()
+        avg = self._has_avg(group)
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         pos = 0
         for lo, hi in sorted(self._done) + [(self.numel, self.numel)]:
             if lo > pos:
-                self._pending.append(dist.all_reduce(self.flat[pos:lo], op=dist.ReduceOp.SUM, group=group,
-                                                     async_op=True))
+                self._pending.append(dist.all_reduce(self.flat[pos:lo], op=op, group=group, async_op=True))
             pos = max(pos, hi)
         for w in self._pending:
             w.wait()
         self._pending, self._done = [], []
-        self.flat.div_(dist.get_world_size(group))
+        if not avg:
+            self.flat.div_(dist.get_world_size(group))
 
     def grad_norm(self):
         self.sync_views()

@@ -387,12 +387,21 @@ def main_ours(args):
     model = CoarseTransformer(**CFG).to(dev).train()
     wrapper = CoarseTransformerWrapper(transformer=model, codec=_CodecStub()).train()  # reference defaults
     bucket = FlatGradBucket(model.parameters()).attach(model)
-    overlap = world > 1 and os.environ.get("ALM_OVERLAP_ALLREDUCE") is not None
+    # default: ONE ncclAvg all-reduce of the flat bucket after the backward.  Overlapping (half / per layer) was measured
+    # at N=2 on B200 and lost both times (profiles/r02_allreduce_n2.md): the persistent GEMMs own all 148 SMs
+    overlap = world > 1 and os.environ.get("ALM_OVERLAP_ALLREDUCE", "0") != "0"
     if overlap:
-        # optional: layer i's slice of the flat bucket is all-reduced (NCCL, its own stream) as soon as its gradients
-        # are final (measured at N=2 in round 1: no gain over ONE all-reduce after the backward)
-        ranges = [bucket.range_of(list(layer.parameters())) for layer in model.transformer.layers]
-        model.transformer.grad_ready_hook = lambda i: bucket.reduce_range_async(*ranges[i])
+        # the upper half of the stack (layers depth/2 .. depth-1: ~half of the bucket) is all-reduced on NCCL's stream
+        # as soon as its gradients are final, under the backward of the lower half; finish() sends the rest.
+        # (ALM_OVERLAP_ALLREDUCE=layers: one collective per layer - measured slower in round 1; =0: single all-reduce)
+        layers = model.transformer.layers
+        ranges = [bucket.range_of(list(layer.parameters())) for layer in layers]
+        if os.environ.get("ALM_OVERLAP_ALLREDUCE") == "layers":
+            model.transformer.grad_ready_hook = lambda i: bucket.reduce_range_async(*ranges[i])
+        else:
+            mid = len(layers) // 2
+            lo, hi = ranges[mid][0], ranges[-1][1]
+            model.transformer.grad_ready_hook = lambda i: bucket.reduce_range_async(lo, hi) if i == mid else None
     n_params = bucket.numel
 
     wsem_h, wco_h = synth_wrapper_ids(BATCH, rank)
@@ -400,6 +409,8 @@ def main_ours(args):
     wsem_d, wco_d = wsem_h.to(dev), wco_h.to(dev)
     sem_d, coarse_d = (t.to(dev) for t in synth_ids(BATCH, rank))
     eos = torch.full((BATCH, 1), CFG["codebook_size"], device=dev)
+
+    NO_COLLECTIVE = os.environ.get("ALM_BENCH_NO_COLLECTIVE") is not None  # diagnostic only: N ranks, no exchange
 
     def prep():
         bucket.zero_()
@@ -413,7 +424,8 @@ def main_ours(args):
         prep()
         loss = wrapper(semantic_token_ids=sem, coarse_token_ids=coarse, return_loss=True)
         loss.backward()
-        bucket.finish()  # N > 1: ONE all-reduce of the flat bucket (+ whatever the overlap hook has not sent) and 1/N
+        if not NO_COLLECTIVE:
+            bucket.finish()  # N > 1: all-reduce of the flat bucket (whatever the overlap hook has not sent yet), mean
         return loss
 
     def step_direct():
@@ -515,6 +527,7 @@ def main_ours(args):
         "e2e": {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": "tokens/s",
                 "h2d_bytes_per_step": (wsem_pin.numel() + wco_pin.numel()) * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
+        **({"diagnostic": "ALM_BENCH_NO_COLLECTIVE: gradient exchange skipped, NOT a valid multi-GPU number"} if NO_COLLECTIVE else {}),
         "clocks": clocks,
         "variants": {"direct_causal": {"tokens_per_s": tokens / (ms_direct * 1e-3), "ms_per_step": ms_direct,
                                        "what": "CoarseTransformer.forward without key mask + the same two CE + bwd"}},
