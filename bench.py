@@ -73,7 +73,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML every 10 ms (pynvml ships with the image as
+    nvidia-ml-py); falls back to polling nvidia-smi when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -82,31 +83,64 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.max_mhz = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices; the UUID of the torch device is authoritative
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(hi)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hi
+            self._h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        mhz = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        names = []
+        for name, bit in (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                          ("sw_power_cap", 0x4)):
+            if r & bit:
+                names.append(name)
+        self.samples.append((mhz, names))
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 7 and f[0].replace(".", "").isdigit():
+                        names = [nm for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                      "sw_power_cap"), f[3:7]) if v.lower().startswith("active")]
+                        self.samples.append((int(float(f[0])), names))
+                        self.max_mhz = int(float(f[1]))
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self._nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(self.samples))
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[1]})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_min_mhz=sm[0] if sm else None,
+                    sm_max_mhz=self.max_mhz, reasons=reasons, samples=len(self.samples),
+                    source="nvml" if self._nvml is not None else "nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -467,7 +501,6 @@ def main_ours(args):
     _lib.reset_launch_count()
     ms_total = timed(lambda: step(wsem_d, wco_d), args.steps)
     launches = _lib.launch_count() / args.steps
-    clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host ids -> device, loss -> host, every step ----
     def e2e_step():
@@ -477,6 +510,7 @@ def main_ours(args):
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if sampler else None   # sampled over both timed regions (device-resident + end-to-end)
 
     # ---- variant (a): no key mask ----
     for _ in range(2):
