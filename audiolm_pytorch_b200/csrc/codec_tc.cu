@@ -174,6 +174,9 @@ struct RuCfg {
   static constexpr int UNIT_BYTES = 2 * 2 * C * 16;  // hi [2 chunks][C][16 B] + lo
   static constexpr int NUNITS = 8 * KSTEPS;
   static constexpr int MAX_NW = 16;
+  // C == 128: the two tiles in flight consume every streamed weight unit TOGETHER (an M = 128 tile alone needs 42.7 B/clk
+  // of weights per SM, the whole chip's L2 throughput; paired tiles halve that).  C == 256 cannot: one tile fills TMEM.
+  static constexpr bool PAIR = C == 128;
   static constexpr int TMEM_COLS = NBUF * 2 * C;
   static constexpr int FIXED_BYTES = 2 * C * 4 + 512 + 128;  // biases, barriers, alignment slack
   static constexpr int MAX_SMEM = 232448;
@@ -183,7 +186,7 @@ template <int C>
 __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(const RuParams p) {
   using Cfg = RuCfg<C>;
   constexpr int NCHUNK = Cfg::NCHUNK, KSTEPS = Cfg::KSTEPS, NBUF = Cfg::NBUF;
-  constexpr bool RESIDENT = Cfg::RESIDENT;
+  constexpr bool RESIDENT = Cfg::RESIDENT, PAIR = Cfg::PAIR;
   const int NA = p.na, NW = p.nw, A_ROWS = p.ar;
   const int A_BYTES = 2 * NCHUNK * A_ROWS * 16;
   extern __shared__ uint8_t smem_raw[];
@@ -232,10 +235,13 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
   auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
   auto has = [&](int i) { return i >= 0 && tile_of(i) < p.total_tiles; };
 
-  if (warp == 0) {
-    // ===================== producer =====================
-    // activation tiles: 16-B cp.async by all 32 lanes (the padding rule is just an address per row); weights: bulk copies
-    if (RESIDENT && lane == 0) {
+  if (warp == 0 || (RESIDENT && warp == 3)) {
+    // ===================== producer(s) =====================
+    // activation tiles: 16-B cp.async by all 32 lanes (the padding rule is just an address per row); weights: bulk copies.
+    // Resident-weight layers (C <= 64) run TWO producer warps, warp 0 owning staging buffer 0 (even tiles) and warp 3
+    // buffer 1 (odd tiles): one warp's address arithmetic + ~90 cp.async per lane per tile left the MMA issuer waiting
+    // on a_full for 20-30 % of its time (profiles/r02_ru_trace_b.txt)
+    if (RESIDENT && warp == 0 && lane == 0) {
       mbar_arrive_expect_tx(&w_full[0], Cfg::NUNITS * Cfg::UNIT_BYTES);
       constexpr int PIECE = 16384;  // few large copies
       for (int off = 0; off < Cfg::NUNITS * Cfg::UNIT_BYTES; off += PIECE)
@@ -292,6 +298,41 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
         prefetch_l2(base + (size_t)c * p.T * 16 + min((size_t)l * 128, span));
       }
     };
+    if (RESIDENT) {
+      const int pid = warp == 0 ? 0 : 1;  // NA == 2: tile i lives in buffer i % 2, owned by producer i % 2
+      if (has(pid + 2)) prefetch_tile(pid + 2);
+      for (int i = pid; has(i); i += 2) {
+        if (has(i + 4)) prefetch_tile(i + 4);
+        issue_a(i);                  // waits until P1(i - 2) has released the buffer
+        cp_async_wait<0>();
+        fence_proxy_async_smem();    // cp.async writes (generic proxy) -> UMMA operand reads (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[i % NA]);
+      }
+    } else if (PAIR) {
+      // tiles 2 ip and 2 ip + 1 are staged together (buffers 0 / 1) and share one pass over the weight units
+      if (has(0)) issue_a(0);
+      if (has(1)) issue_a(1);
+      for (int i0 = 0; has(i0); i0 += 2) {
+        if (has(i0 + 2)) prefetch_tile(i0 + 2);
+        if (has(i0 + 3)) prefetch_tile(i0 + 3);
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[0]);
+          if (has(i0 + 1)) mbar_arrive(&a_full[1]);
+          stream_units(0, 7 * KSTEPS);
+        }
+        __syncwarp();
+        // next pair's activations: the buffers are released by the commit after P1 of this pair; the copies then run
+        // under E1 / P2 / E2 of this pair
+        if (has(i0 + 2)) issue_a(i0 + 2);
+        if (has(i0 + 3)) issue_a(i0 + 3);
+        if (lane == 0) stream_units(7 * KSTEPS, 8 * KSTEPS);
+        __syncwarp();
+      }
+    } else {
     if (has(0)) issue_a(0);
     for (int k = 1; k < PF; ++k)
       if (has(k)) prefetch_tile(k);
@@ -317,6 +358,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
         __syncwarp();
       }
     }
+    }
   } else if (warp == 1) {
     {
       // ===================== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues =======
@@ -328,6 +370,88 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
       int wstage = 0;
       uint32_t wphase = 0;
       const uint32_t sw_addr = smem_u32(sW);
+      if constexpr (PAIR) {
+        const uint64_t b0 = umma_smem_desc_nosw(sw_addr, 128, C * 16);
+        const uint32_t kstep_units = 2 * A_ROWS;
+        for (int i0 = 0; has(i0); i0 += 2) {
+          const bool two = has(i0 + 1);
+          const uint32_t ph = ((uint32_t)(i0 / 2)) & 1u;   // buffers 0 / 1 are used once per pair
+          RU_TRACE_WAIT(0, mbar_wait(&a_full[0], ph));
+          if (two) mbar_wait(&a_full[1], ph);
+          tc_fence_after_sync();
+          uint64_t a_hi0[2], a_lo0[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t a_addr = smem_u32(sA + t * A_BYTES);
+            a_hi0[t] = umma_smem_desc_nosw(a_addr, 128, A_ROWS * 16);
+            a_lo0[t] = umma_smem_desc_nosw(a_addr + NCHUNK * (A_ROWS * 16), 128, A_ROWS * 16);
+          }
+          const uint32_t d1a = tmem_base, d1b = tmem_base + 2 * C;
+#pragma unroll 1
+          for (int j = 0; j < 7; ++j) {
+            const uint32_t row_units = (uint32_t)(j * p.d);
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              RU_TRACE_WAIT(3, mbar_wait(&w_full[wstage], wphase));
+              tc_fence_after_sync();
+              const uint64_t b_hi = b0 + (uint64_t)(wstage * (Cfg::UNIT_BYTES / 16));
+              const uint64_t b_lo = b_hi + (uint64_t)(2 * C);
+              const uint64_t off = (uint64_t)(kk * kstep_units + row_units);
+              const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+              if (elect_one_sync()) {
+                umma_bf16_ss(d1a, a_hi0[0] + off, b_hi, idesc, acc);
+                umma_bf16_ss(d1a, a_lo0[0] + off, b_hi, idesc, 1u);
+                umma_bf16_ss(d1a, a_hi0[0] + off, b_lo, idesc, 1u);
+                if (two) {
+                  umma_bf16_ss(d1b, a_hi0[1] + off, b_hi, idesc, acc);
+                  umma_bf16_ss(d1b, a_lo0[1] + off, b_hi, idesc, 1u);
+                  umma_bf16_ss(d1b, a_hi0[1] + off, b_lo, idesc, 1u);
+                }
+                umma_commit(&w_empty[wstage]);
+              }
+              if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
+            }
+          }
+          if (elect_one_sync()) {
+            umma_commit(&a_empty[0]);
+            umma_commit(&d1_full[0]);
+            if (two) {
+              umma_commit(&a_empty[1]);
+              umma_commit(&d1_full[1]);
+            }
+          }
+          RU_TRACE_WAIT(1, mbar_wait(&a2_full[0], ph));
+          RU_TRACE_WAIT(2, mbar_wait(&d2_empty[0], ph ^ 1u));
+          if (two) {
+            mbar_wait(&a2_full[1], ph);
+            mbar_wait(&d2_empty[1], ph ^ 1u);
+          }
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            mbar_wait(&w_full[wstage], wphase);
+            tc_fence_after_sync();
+            const uint64_t b_hi = b0 + (uint64_t)(wstage * (Cfg::UNIT_BYTES / 16));
+            const uint64_t b_lo = b_hi + (uint64_t)(2 * C);
+            if (elect_one_sync()) {
+              umma_bf16_ts(d1a + C, d1a + 16 * kk, b_hi, idesc, kk > 0 ? 1u : 0u);
+              umma_bf16_ts(d1a + C, d1a + 16 * kk + 8, b_hi, idesc, 1u);
+              umma_bf16_ts(d1a + C, d1a + 16 * kk, b_lo, idesc, 1u);
+              if (two) {
+                umma_bf16_ts(d1b + C, d1b + 16 * kk, b_hi, idesc, kk > 0 ? 1u : 0u);
+                umma_bf16_ts(d1b + C, d1b + 16 * kk + 8, b_hi, idesc, 1u);
+                umma_bf16_ts(d1b + C, d1b + 16 * kk, b_lo, idesc, 1u);
+              }
+              umma_commit(&w_empty[wstage]);
+            }
+            if (++wstage == NW) { wstage = 0; wphase ^= 1u; }
+          }
+          if (elect_one_sync()) {
+            umma_commit(&d2_full[0]);
+            if (two) umma_commit(&d2_full[1]);
+          }
+        }
+      } else
       for (int i = 0;; ++i) {
         const int i2 = i - (NBUF - 1);
         const bool h1 = has(i), h2 = has(i2);
@@ -428,11 +552,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
     const int q = ew & 3, sub = ew >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    for (int i = 0;; ++i) {
-      const int i2 = i - (NBUF - 1);
-      const bool h1 = has(i), h2 = has(i2);
-      if (!h1 && !h2) break;
-      if (h1) {
+    auto e1 = [&](const int i) {
         // ---- E1: D1 -> (+b7, ELU, split) -> the same columns as the packed bf16 A operand of the 1x1 conv ----
         const int tb = i % NBUF;
         if (warp == 4 && lane == 0) { RU_TRACE_WAIT(4, mbar_wait(&d1_full[tb], ((uint32_t)(i / NBUF)) & 1u)); } else mbar_wait(&d1_full[tb], ((uint32_t)(i / NBUF)) & 1u);
@@ -450,8 +570,8 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a2_full[tb]);
-      }
-      if (h2) {
+    };
+    auto e2 = [&](const int i2) {
         // ---- E2: D2 -> (+b1, ELU, + skip) -> split -> global (C8S) ----
         const int tb = i2 % NBUF;
         const int tile = tile_of(i2);
@@ -504,6 +624,23 @@ __global__ void __launch_bounds__(CTA_THREADS, (C <= 32 ? 2 : 1)) ru_tc_kernel(c
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d2_empty[tb]);
+    };
+    if constexpr (PAIR) {
+      // both tiles of a pair through E1 first (the paired 1x1-conv MMAs wait for both), then both through E2
+      for (int i0 = 0; has(i0); i0 += 2) {
+        const bool two = has(i0 + 1);
+        e1(i0);
+        if (two) e1(i0 + 1);
+        e2(i0);
+        if (two) e2(i0 + 1);
+      }
+    } else {
+      for (int i = 0;; ++i) {
+        const int i2 = i - (NBUF - 1);
+        const bool h1 = has(i), h2 = has(i2);
+        if (!h1 && !h2) break;
+        if (h1) e1(i);
+        if (h2) e2(i2);
       }
     }
   }
@@ -531,7 +668,7 @@ static int launch_ru(RuParams p, cudaStream_t stream) {
     auto stages = [&](int na) {
       return min(Cfg::MAX_NW, (Cfg::MAX_SMEM - na * a_bytes - Cfg::FIXED_BYTES) / Cfg::UNIT_BYTES);
     };
-    p.na = (Cfg::NBUF == 2 && stages(2) * Cfg::UNIT_BYTES >= 48 * 1024) ? 2 : 1;
+    p.na = (Cfg::PAIR || (Cfg::NBUF == 2 && stages(2) * Cfg::UNIT_BYTES >= 48 * 1024)) ? 2 : 1;
     p.nw = stages(p.na);
     if (p.nw < 2) return ALM_ERR_UNSUPPORTED;
     smem = p.na * a_bytes + p.nw * Cfg::UNIT_BYTES + Cfg::FIXED_BYTES;
@@ -572,7 +709,7 @@ struct ConvCfg {
   static constexpr int W_BYTES = 4 * BN * 16;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = BN == 256 ? 8 : 10;
-  static constexpr int LOOKAHEAD = 5;                   // cp.async groups in flight before the oldest is published
+  static constexpr int LOOKAHEAD = 3;                   // cp.async groups in flight PER PRODUCER WARP before its oldest is published
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + 128;
 };
@@ -620,15 +757,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParam
     b = r / p.m_tiles;
   };
 
-  if (warp == 0) {
-    // ===================== producer (all 32 lanes) =====================
-    int stage = 0, done_stage = 0, pending = 0;
+  if (warp == 0 || warp == 3) {
+    // ===================== two producer warps (all 32 lanes each): warp 0 stages the even units, warp 3 the odd ones
+    // (one warp's address arithmetic + issue of 16 cp.async per stage could not keep the small-N layers fed:
+    // profiles/r02_ncu_codec_summary.md, conv_tc_kernel<64> at 7 % tensor-pipe activity) =====================
+    const int pid = warp == 0 ? 0 : 1;
+    int stage = 0, pending = 0, k = 0, done_m = 0;
     uint32_t phase = 0;
-    auto publish_oldest = [&]() {  // the oldest cp.async group has landed: make it visible to the UMMA, signal
+    auto publish_oldest = [&]() {  // this warp's oldest cp.async group has landed: make it visible to the UMMA, signal
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[done_stage]);
-      if (++done_stage == STAGES) done_stage = 0;
+      if (lane == 0) mbar_arrive(&full[(2 * done_m + pid) % STAGES]);
+      ++done_m;
       --pending;
     };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -637,26 +777,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParam
       const int t0 = mt * TILE_M;
       const int nrows = min(TILE_M, p.n_out - t0);
       const __nv_bfloat16* xb = p.x + (size_t)b * 2 * nch * p.s * (size_t)rows_in * 8;
-      {
-        // the stage ring holds ~1 us of MMA work, less than the HBM latency under load: pull the NEXT tile's input rows
-        // (every plane, every chunk) into L2 while this tile streams
-        const int ntile = tile + (int)gridDim.x;
-        if (ntile < p.total_tiles) {
-          int nb, nmt, nnt;
-          decode(ntile, nb, nmt, nnt);
-          if (nnt == 0 || p.n_tiles == 1) {
-            const int r0 = max(0, nmt * TILE_M - 2), r1 = min(rows_in, nmt * TILE_M + TILE_M + 1);
-            const int lpc = ((r1 - r0) * 16 + 127) / 128 + 1;
-            const uint8_t* base = reinterpret_cast<const uint8_t*>(p.x + ((size_t)nb * 2 * nch * p.s * (size_t)rows_in + r0) * 8);
-            const size_t span = (size_t)(r1 - r0) * 16 - 1;
-            const int planes = 2 * nch * p.s;
-            for (int idx = lane; idx < planes * lpc; idx += 32) {
-              const int pl = idx / lpc, l = idx - pl * lpc;
-              prefetch_l2(base + (size_t)pl * rows_in * 16 + min((size_t)l * 128, span));
-            }
-          }
-        }
-      }
+      // (an L2 prefetch of the next tile's rows was tried here and made every layer slower: profiles/r02_codec_layers_c.txt)
       for (int j = 0; j < p.K; ++j) {
         const int q = j - pad;
         const int plane = ((q % p.s) + p.s) % p.s;
@@ -678,7 +799,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParam
           src_row[it] = ((size_t)pl * rows_in + rw) * 8;
           src_bytes[it] = bytes;
         }
-        for (int kk = 0; kk < ksteps; ++kk) {
+        for (int kk = 0; kk < ksteps; ++kk, ++k) {
+          if ((k & 1) != pid) {  // the other producer's unit
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
 #pragma unroll
