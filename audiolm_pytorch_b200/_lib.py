@@ -50,7 +50,9 @@ SIGNATURES: dict[str, list] = {
     "alm_causal_convT1d_fwd": [P, P, P, P, I, I, I, I, I, P],
     "alm_codec_first_conv": [P, P, P, P, I, I, I, I, I, P],
     "alm_codec_ru_tc": [P, P, P, P, P, I, I, I, I, I, I, P],
-    "alm_codec_conv_tc": [P, P, P, P, I, I, I, I, I, I, I, I, I, P],
+    "alm_codec_conv_tc": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "alm_codec_pack_c8s": [P, P, I, I, I, P],
+    "alm_codec_last_conv": [P, P, P, P, I, I, I, I, I, P],
     "alm_rvq_encode": [P, L, P, P, P, L, P, L, I, I, I, I, P],
     "alm_rvq_pack_codebooks": [P, P, P, L, I, P],
     "alm_rvq_prepare": [P, L, P, P, L, P, I, I, P],

@@ -121,6 +121,65 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 channels-last [B][n][C] (the quantizer's output) -> C8S (P = 1): the decoder's entry format
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_c8s_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B,
+                                                       int n, int C) {
+  const int nch = C / 8;
+  const long long total = (long long)B * n * nch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nch);
+    const long long bt = i / nch;
+    const int t = (int)(bt % n), b = (int)(bt / n);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + bt * C + c * 8));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + bt * C + c * 8 + 4));
+    const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(y + c8s_off(b, c, t, 2 * nch, 1, n)) = hi;
+    *reinterpret_cast<uint4*>(y + c8s_off(b, nch + c, t, 2 * nch, 1, n)) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// last decoder conv: CausalConv1d(CIN, 1, K <= 8) on C8S -> fp32 wave [B][T] (soundstream.py:626), CUDA cores
+// ---------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(128) last_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                        int T, int K, int pad_mode) {
+  __shared__ float sw[CIN * 8];  // [ci][tap]
+  for (int i = threadIdx.x; i < CIN * 8; i += blockDim.x) sw[i] = (i % 8) < K ? w[(i / 8) * K + (i % 8)] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  constexpr int NCH = CIN / 8;
+  const int pad = K - 1;
+  float acc = bias ? bias[0] : 0.f;
+  for (int j = 0; j < K; ++j) {
+    int u = t + j - pad;
+    if (u < 0) {
+      if (pad_mode == 0) u = -u;
+      else if (pad_mode == 2) u = 0;
+      else continue;
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(x + c8s_off(b, c, u, 2 * NCH, 1, T)));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(x + c8s_off(b, NCH + c, u, 2 * NCH, 1, T)));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc = fmaf(sw[(c * 8 + 2 * e) * 8 + j], bf16_lo(hw[e]) + bf16_lo(lw[e]), acc);
+        acc = fmaf(sw[(c * 8 + 2 * e + 1) * 8 + j], bf16_hi(hw[e]) + bf16_hi(lw[e]), acc);
+      }
+    }
+  }
+  y[(size_t)b * T + t] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // shared pieces
 // ---------------------------------------------------------------------------------------------
 constexpr int NEW = 8;                       // epilogue warps (two per TMEM lane quadrant)
@@ -700,6 +759,7 @@ struct ConvParams {
   const __nv_bfloat16* w;   // [ntile][tap][kstep][part][2][BN][8]
   const float* bias;
   int B, Cin, Cout, Tin, n_out, K, s, pad_mode, out_phases, out_fp32;
+  int up;  // > 1: the Cout = up * C' output columns are `up` consecutive time steps of C' channels (transposed conv)
   int m_tiles, n_tiles, total_tiles;
 };
 
@@ -899,6 +959,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) conv_tc_kernel(const ConvParam
 #pragma unroll
             for (int e = 0; e < 16; e += 4)
               *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          } else if (p.up > 1) {
+            // CausalConvTranspose1d as a 2-tap conv with up * C' output columns: column block r is output time t * up + r
+            __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
+            const int creal = p.Cout / p.up, r_ = ch0 / creal, cbase = ch0 - r_ * creal;
+            const size_t t_out = (size_t)t * p.up + r_, T_out = (size_t)p.n_out * p.up;
+            const int nchr = creal / 8;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], oh[e], ol[e]);
+              const int chunk = cbase / 8 + c;
+              *reinterpret_cast<uint4*>(yb + (((size_t)b * 2 * nchr + chunk) * T_out + t_out) * 8) =
+                  make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4*>(yb + (((size_t)b * 2 * nchr + nchr + chunk) * T_out + t_out) * 8) =
+                  make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            }
           } else {
             __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
 #pragma unroll
@@ -990,16 +1067,19 @@ extern "C" int alm_codec_ru_tc(const void* x, void* y, const void* w_units, cons
 
 extern "C" int alm_codec_conv_tc(const void* x, void* y, const void* w_units, const float* bias, int B, int Cin,
                                  int Cout, int Tin, int K, int stride, int pad_mode, int out_phases, int out_fp32,
-                                 alm_stream_t stream_) {
+                                 int upsample, alm_stream_t stream_) {
   using namespace alm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(x && y && w_units && B > 0 && Tin > 0, ALM_ERR_ARG);
   ALM_REQUIRE(Cin % 16 == 0 && K >= stride && stride >= 1 && Tin % stride == 0, ALM_ERR_UNSUPPORTED);
   ALM_REQUIRE(pad_mode >= 0 && pad_mode <= 2, ALM_ERR_UNSUPPORTED);
   ALM_REQUIRE(Tin > K, ALM_ERR_ARG);
-  const int BN = Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64);
+  const int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   ALM_REQUIRE(Cout % BN == 0, ALM_ERR_UNSUPPORTED);
+  ALM_REQUIRE(upsample >= 1 && Cout % upsample == 0 && (upsample == 1 || ((Cout / upsample) % 16 == 0 && !out_fp32)),
+              ALM_ERR_UNSUPPORTED);
   ctc::ConvParams p;
+  p.up = upsample;
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.y = y;
   p.w = reinterpret_cast<const __nv_bfloat16*>(w_units);
@@ -1027,3 +1107,32 @@ extern "C" int alm_debug_ru_trace(unsigned long long* out16, int reset) {
   return 0;
 }
 #endif
+
+extern "C" int alm_codec_pack_c8s(const float* x, void* y, int B, int n, int C, alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(x && y && B > 0 && n > 0 && C > 0 && C % 8 == 0, ALM_ERR_ARG);
+  const long long total = (long long)B * n * (C / 8);
+  const long long want_blocks = (total + 255) / 256;
+  const int grid = (int)(want_blocks < 148 * 16 ? want_blocks : 148 * 16);
+  ctc::pack_c8s_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), B, n, C);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
+extern "C" int alm_codec_last_conv(const void* x, const float* w, const float* bias, float* y, int B, int T, int Cin,
+                                   int K, int pad_mode, alm_stream_t stream_) {
+  using namespace alm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(x && w && y && B > 0 && T > 0, ALM_ERR_ARG);
+  ALM_REQUIRE(K >= 1 && K <= 8 && pad_mode >= 0 && pad_mode <= 2 && T > K - 1, ALM_ERR_UNSUPPORTED);
+  dim3 grid(ceil_div(T, 128), B);
+  const __nv_bfloat16* xx = reinterpret_cast<const __nv_bfloat16*>(x);
+  if (Cin == 32) ctc::last_conv_kernel<32><<<grid, 128, 0, stream>>>(xx, w, bias, y, B, T, K, pad_mode);
+  else if (Cin == 64) ctc::last_conv_kernel<64><<<grid, 128, 0, stream>>>(xx, w, bias, y, B, T, K, pad_mode);
+  else return ALM_ERR_UNSUPPORTED;
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}

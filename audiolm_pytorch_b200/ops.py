@@ -528,11 +528,45 @@ def pack_ru_weights(w7, w1):
 
 
 def conv_tc_bn(cout):
-    return 256 if cout >= 256 else (128 if cout >= 128 else 64)
+    return 256 if cout % 256 == 0 else (128 if cout % 128 == 0 else 64)
 
 
 def pack_conv_weights(w):
     return _split_units(w.detach().float(), bn=conv_tc_bn(w.shape[0]))
+
+
+def pack_convT_weights(w, stride):
+    """CausalConvTranspose1d weight [Cin, Cout, 2s] -> (units for alm_codec_conv_tc, Cout' = s * Cout): the transposed conv
+    is the 2-tap causal conv  out[i, (r, o)] = W[c, o, r + s] x[i - 1, c] + W[c, o, r] x[i, c]  (soundstream.py:347-360)."""
+    cin, cout, k = w.shape
+    assert k == 2 * stride
+    wf = w.detach().float()
+    taps = torch.stack((wf[..., stride:], wf[..., :stride]), dim=-1)          # [c, o, r, j]: j = 0 -> x[i-1], 1 -> x[i]
+    wp = taps.permute(2, 1, 0, 3).reshape(stride * cout, cin, 2)               # [(r, o), c, j]
+    return pack_conv_weights(wp)
+
+
+def codec_pack_c8s(x):
+    """fp32 channels-last [B, n, C] -> C8S [B, 2C/8, 1, n, 8] (entry of the tensor-core decoder)."""
+    _check_cuda(x)
+    B, n, C = x.shape
+    x = x.to(f32).contiguous()
+    y = torch.empty(B, 2 * C // 8, 1, n, 8, device=x.device, dtype=bf16)
+    _lib.call("alm_codec_pack_c8s", x, y, B, n, C)
+    return y
+
+
+def codec_last_conv(x, weight, bias, *, pad_mode="reflect"):
+    """CausalConv1d(Cin, 1, K) on C8S (P = 1) -> fp32 [B, 1, T] (soundstream.py:626)."""
+    _check_cuda(x, weight, bias)
+    B, nch2, P, T, _ = x.shape
+    assert P == 1 and weight.shape[0] == 1 and weight.shape[1] == nch2 * 4
+    y = torch.empty(B, 1, T, device=x.device, dtype=f32)
+    with _timed("codec_last_conv", 4.0 * B * T * (nch2 * 4 + 1), "byte"):
+        _lib.call("alm_codec_last_conv", x, weight.detach().contiguous(),
+                  None if bias is None else bias.detach().contiguous(), y, B, T, nch2 * 4, weight.shape[2],
+                  PAD_MODES[pad_mode])
+    return y
 
 
 def codec_first_conv(wave, weight, bias, *, pad_mode="reflect"):
@@ -565,8 +599,10 @@ def codec_ru_tc(x, w_units, b7, b1, *, dilation, pad_mode="reflect", out_phases=
     return y
 
 
-def codec_conv_tc(x, w_units, bias, *, cout, kernel_size, stride, pad_mode="reflect", out_phases=1, out_fp32=False):
-    """CausalConv1d(Cin, cout, kernel_size, stride) on C8S activations with P = stride planes."""
+def codec_conv_tc(x, w_units, bias, *, cout, kernel_size, stride, pad_mode="reflect", out_phases=1, out_fp32=False,
+                  upsample=1):
+    """CausalConv1d(Cin, cout, kernel_size, stride) on C8S activations with P = stride planes.  upsample = s > 1: the
+    transposed-conv form (see pack_convT_weights): cout = s * C' columns become s time steps of C' channels."""
     _check_cuda(x, w_units, bias)
     B, nch2, P, Tp, _ = x.shape
     Cin, Tin = nch2 * 4, P * Tp
@@ -574,6 +610,8 @@ def codec_conv_tc(x, w_units, bias, *, cout, kernel_size, stride, pad_mode="refl
     n_out = Tin // stride
     if out_fp32:
         y = torch.empty(B, n_out, cout, device=x.device, dtype=f32)
+    elif upsample > 1:
+        y = torch.empty(B, 2 * (cout // upsample) // 8, 1, n_out * upsample, 8, device=x.device, dtype=bf16)
     else:
         y = torch.empty(B, 2 * cout // 8, out_phases, n_out // out_phases, 8, device=x.device, dtype=bf16)
     cls = "codec_conv_tc"
@@ -581,7 +619,7 @@ def codec_conv_tc(x, w_units, bias, *, cout, kernel_size, stride, pad_mode="refl
         cls += f" Cin{Cin} Cout{cout} K{kernel_size} s{stride} T{Tin}"
     with _timed(cls, 4.0 * B * (Cin * Tin + cout * n_out), "byte"):
         _lib.call("alm_codec_conv_tc", x, y, w_units, bias, B, Cin, cout, Tin, int(kernel_size), int(stride),
-                  PAD_MODES[pad_mode], int(out_phases), int(out_fp32))
+                  PAD_MODES[pad_mode], int(out_phases), int(out_fp32), int(upsample))
     return y
 
 

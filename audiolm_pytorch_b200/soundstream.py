@@ -330,6 +330,60 @@ class SoundStream(nn.Module):
         return ops.codec_conv_tc(h, wu, last.conv.bias, cout=last.conv.out_channels,
                                  kernel_size=last.conv.kernel_size[0], stride=1, pad_mode=last.pad_mode, out_fp32=True)
 
+    def _tc_plan_dec(self):
+        """layer list for the tensor-core decoder (soundstream.py:615-627) or None"""
+        if not (ENCODER_ON_TENSOR_CORES and self.single_channel):
+            return None
+        dec = list(self.decoder)
+        first, blocks, last = dec[0], dec[1:-1], dec[-1]
+        ok = (isinstance(first, CausalConv1d) and first.stride == 1 and first.dilation == 1
+              and first.conv.in_channels % 16 == 0 and first.conv.out_channels % 64 == 0
+              and isinstance(last, CausalConv1d) and last.conv.out_channels == 1 and last.conv.in_channels in (32, 64)
+              and last.conv.kernel_size[0] <= 8 and last.stride == 1 and last.dilation == 1)
+        plan = []
+        for blk in blocks if ok else ():
+            up, *rus = list(blk)
+            ok = ok and isinstance(up, CausalConvTranspose1d) and up.conv.in_channels % 16 == 0 \
+                and up.conv.out_channels % 16 == 0 and (up.upsample_factor * up.conv.out_channels) % 64 == 0
+            for ru in rus:
+                c7, c1 = getattr(ru.fn, "0"), getattr(ru.fn, "2")
+                C = c7.conv.in_channels
+                ok = ok and (C in (32, 64, 128, 256) and c7.conv.out_channels == C and c7.conv.kernel_size[0] == 7
+                             and c1.conv.kernel_size[0] == 1 and 6 * c7.dilation <= 54 and c7.stride == 1)
+            plan.append((up, rus))
+        return (first, plan, last) if ok else None
+
+    def _decode_tc(self, x, plan):
+        """x fp32 [B, n, codebook_dim] channels-last -> wave [B, 1, n * prod(strides)]; C8S between layers"""
+        first, blocks, last = plan
+        h = ops.codec_pack_c8s(x)
+        wu = self._cached(first, "_tc_units", [first.conv.weight], lambda: ops.pack_conv_weights(first.conv.weight))
+        h = ops.codec_conv_tc(h, wu, first.conv.bias, cout=first.conv.out_channels,
+                              kernel_size=first.conv.kernel_size[0], stride=1, pad_mode=first.pad_mode)
+        for up, rus in blocks:
+            s_ = up.upsample_factor
+            wu = self._cached(up, "_tc_units", [up.conv.weight],
+                              lambda up=up, s_=s_: ops.pack_convT_weights(up.conv.weight, s_))
+            bias_up = self._cached(up, "_tc_bias", [up.conv.bias],
+                                   lambda up=up, s_=s_: up.conv.bias.detach().float().repeat(s_).contiguous())
+            h = ops.codec_conv_tc(h, wu, bias_up, cout=s_ * up.conv.out_channels, kernel_size=2, stride=1,
+                                  pad_mode="constant", upsample=s_)
+            for ru in rus:
+                c7, c1 = getattr(ru.fn, "0"), getattr(ru.fn, "2")
+                wr = self._cached(ru, "_tc_units", [c7.conv.weight, c1.conv.weight],
+                                  lambda c7=c7, c1=c1: ops.pack_ru_weights(c7.conv.weight, c1.conv.weight))
+                h = ops.codec_ru_tc(h, wr, c7.conv.bias, c1.conv.bias, dilation=c7.dilation, pad_mode=c7.pad_mode)
+        return ops.codec_last_conv(h, last.conv.weight, last.conv.bias, pad_mode=last.pad_mode)
+
+    def decode_frames(self, x):
+        """x [B, n, codebook_dim] channels-last (quantized) -> wave [B, 1, T] (soundstream.py:859-861)"""
+        plan = self._tc_plan_dec()
+        n = x.shape[1]
+        # the first residual units see n x first upsampling factor samples and need more than their reflect halo
+        if plan is not None and x.is_cuda and n >= 8 and n * plan[1][0][0].upsample_factor > 54:
+            return self._decode_tc(x, plan)
+        return self.decoder(x.transpose(1, 2).contiguous())
+
     def encode_frames(self, x):
         """x [B, 1, T] fp32 -> encoder output [B, n, codebook_dim] channels-last (soundstream.py:827-836)."""
         plan = self._tc_plan()
@@ -366,7 +420,7 @@ class SoundStream(nn.Module):
             x, *_ = self.rq(x)
         if exists(self.decoder_attn):
             x = self.decoder_attn(x)
-        return self.decoder(x.transpose(1, 2).contiguous())
+        return self.decode_frames(x)
 
     @torch.no_grad()
     def tokenize(self, audio):
@@ -390,7 +444,7 @@ class SoundStream(nn.Module):
             return quantized, indices.permute(1, 2, 0, 3).reshape(b, n, g * q), commit_loss
         if exists(self.decoder_attn):
             quantized = self.decoder_attn(quantized)
-        recon = self.decoder(quantized.transpose(1, 2).contiguous())
+        recon = self.decode_frames(quantized)
         if return_recons_only:
             return recon.reshape(*lead, *recon.shape[-2:]) if len(lead) != 1 else recon
         raise NotImplementedError("SoundStream training losses (GAN / mel / feature matching) are outside this build")

@@ -260,7 +260,17 @@ int alm_codec_first_conv(const float* x, const float* w, const float* bias, void
 int alm_codec_ru_tc(const void* x, void* y, const void* w_units, const float* b7, const float* b1, int B, int C, int T,
                     int dilation, int pad_mode, int out_phases, alm_stream_t stream);
 int alm_codec_conv_tc(const void* x, void* y, const void* w_units, const float* bias, int B, int Cin, int Cout, int Tin,
-                      int K, int stride, int pad_mode, int out_phases, int out_fp32, alm_stream_t stream);
+                      int K, int stride, int pad_mode, int out_phases, int out_fp32, int upsample, alm_stream_t stream);
+/*
+ * Decoder side (soundstream.py:347-360, 615-627).  CausalConvTranspose1d(Cin, C', 2s, stride s) runs as
+ * alm_codec_conv_tc with K = 2, stride 1, constant padding, Cout = s * C' (ops.pack_convT_weights) and upsample = s:
+ * output column block r of row t is written as time step t * s + r of a C8S tensor with C' channels.
+ * alm_codec_pack_c8s: fp32 channels-last [B][n][C] (quantizer output) -> C8S (P = 1).
+ * alm_codec_last_conv: CausalConv1d(Cin in {32, 64}, 1, K <= 8) on C8S -> fp32 wave [B][T].
+ */
+int alm_codec_pack_c8s(const float* x, void* y, int B, int n, int C, alm_stream_t stream);
+int alm_codec_last_conv(const void* x, const float* w, const float* bias, float* y, int B, int T, int Cin, int K,
+                        int pad_mode, alm_stream_t stream);
 int alm_causal_convT1d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
                            int n, int stride, alm_stream_t stream);
 /*

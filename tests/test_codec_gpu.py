@@ -290,3 +290,59 @@ def test_kmeans_nearest_centroid_vs_cdist():
     safe = (top2[:, 1] - top2[:, 0]) > 1e-4
     ids = ops.nearest_centroid(x.to(DEV), ops.rvq_pack_codebooks(centers[None].to(DEV))).cpu()
     assert safe.float().mean() > 0.99 and torch.equal(ids[safe], ref[safe])
+
+
+@pytest.mark.parametrize("cin,cout,s,n", [(512, 256, 8, 150), (256, 128, 5, 1200), (128, 64, 4, 700), (64, 32, 2, 3000)])
+def test_conv_transpose_tc_vs_oracle(cin, cout, s, n):
+    """CausalConvTranspose1d as the 2-tap tensor-core conv with s * Cout columns scattered to s time steps"""
+    from audiolm_pytorch_b200 import ops
+    from oracle import codec as oc
+
+    g = torch.Generator().manual_seed(cin + s)
+    w = torch.randn(cin, cout, 2 * s, generator=g) * (0.7 / (2 * cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(2, cin, n, generator=g)
+    ref = oc.causal_conv_transpose1d(x, w, b, s)
+    xc = ops.c8s_pack(x.to(DEV))
+    y = ops.codec_conv_tc(xc, ops.pack_convT_weights(w.to(DEV), s), b.to(DEV).repeat(s).contiguous(), cout=s * cout,
+                          kernel_size=2, stride=1, pad_mode="constant", upsample=s)
+    got = ops.c8s_unpack(y)
+    assert got.shape == ref.shape and err(got, ref) < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_decoder_edge_kernels_tc():
+    """fp32 channels-last -> C8S packing and the last CausalConv1d(32, 1, 7) -> fp32 wave"""
+    from audiolm_pytorch_b200 import ops
+    from oracle import codec as oc
+
+    g = torch.Generator().manual_seed(4)
+    q = torch.randn(2, 150, 512, generator=g)
+    packed = ops.codec_pack_c8s(q.to(DEV))
+    assert err(ops.c8s_unpack(packed), q.transpose(1, 2)) < 2e-5 * q.abs().max().item()
+    x = torch.randn(2, 32, 5000, generator=g)
+    w, b = torch.randn(1, 32, 7, generator=g) * 0.1, torch.randn(1, generator=g)
+    for mode in ("reflect", "constant"):
+        ref = oc.causal_conv1d(x, w, b, pad_mode=mode)
+        y = ops.codec_last_conv(ops.c8s_pack(x.to(DEV)), w.to(DEV), b.to(DEV), pad_mode=mode)
+        assert y.shape == ref.shape and err(y, ref) < 5e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_c1_decoder_vs_oracle():
+    """full C1 decoder (512 x 150 frames -> 48 000 samples) on the tensor-core path vs the oracle"""
+    from audiolm_pytorch_b200.soundstream import SoundStream
+    from oracle import codec as oc
+    from oracle.transformer import sub
+
+    torch.manual_seed(13)
+    ss = SoundStream(codebook_size=1024, rq_num_quantizers=8, target_sample_hz=24000, use_local_attn=False)
+    st = {k: v.detach().clone() for k, v in ss.state_dict().items()}
+    q = torch.randn(2, 150, 512) * 0.5
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    ref = oc.decoder(sub(st, "decoder"), q.transpose(1, 2))
+    ss = ss.to(DEV).eval()
+    assert ss._tc_plan_dec() is not None
+    with torch.no_grad():
+        got = ss.decode(q.to(DEV))
+    e, scale = err(got, ref), ref.abs().max().item()
+    print(f"C1 decoder max abs err {e:.3e} (scale {scale:.3f})")
+    assert got.shape == ref.shape == (2, 1, 48000) and e < 2e-4 * max(1.0, scale)
