@@ -37,7 +37,9 @@ def hc_ref(hc, ln_gamma, R, d):
     return mix[:, 1:], bin_, xn, beta
 
 
-@pytest.mark.parametrize("M,d,expand", [(37, 64, False), (300, 1024, False), (64, 128, True), (200, 1024, True)])
+# d = 1536 / 2048 run the first-generation kernels of hyper_conn.cu (the only ones that take d > 1024)
+@pytest.mark.parametrize("M,d,expand", [(37, 64, False), (300, 1024, False), (64, 128, True), (200, 1024, True),
+                                        (130, 1536, False), (66, 2048, True)])
 def test_hc_pre_fwd_bwd(M, d, expand):
     from audiolm_pytorch_b200 import ops
 
@@ -89,7 +91,7 @@ def test_hc_pre_fwd_bwd(M, d, expand):
     assert rel_err(g_ln, lng_leaf.grad) < 3e-2
 
 
-@pytest.mark.parametrize("M,d", [(50, 64), (300, 1024)])
+@pytest.mark.parametrize("M,d", [(50, 64), (300, 1024), (70, 1536)])
 def test_hc_post_fwd_bwd(M, d):
     from audiolm_pytorch_b200 import ops
 
