@@ -626,12 +626,19 @@ hc_post_bwd_kernel(const __nv_bfloat16* __restrict__ R_in, const __nv_bfloat16* 
 
 static inline int hc_threads(int d) { return ((d / 8 + 31) / 32) * 32; }
 // launch kernel template K<MAXT> with the smallest MAXT in {128,256,512,1024} that covers `threads`
-#define HC_DISPATCH(K, grid, threads, smem, stream, ...)                                   \
-  do {                                                                                     \
-    if ((threads) <= 128) K<128><<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__);      \
-    else if ((threads) <= 256) K<256><<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__); \
-    else if ((threads) <= 512) K<512><<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__); \
-    else K<1024><<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__);                      \
+// (dims above 1024 need more than the default 48 KB of dynamic shared memory: opt in per instantiation)
+#define HC_LAUNCH_ONE(K, T_, grid, threads, smem, stream, ...)                                             \
+  do {                                                                                                     \
+    if ((size_t)(smem) > 48 * 1024)                                                                        \
+      ALM_CUDA_OK(cudaFuncSetAttribute(K<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));  \
+    K<T_><<<(grid), (threads), (smem), (stream)>>>(__VA_ARGS__);                                           \
+  } while (0)
+#define HC_DISPATCH(K, grid, threads, smem, stream, ...)                                      \
+  do {                                                                                        \
+    if ((threads) <= 128) HC_LAUNCH_ONE(K, 128, grid, threads, smem, stream, __VA_ARGS__);      \
+    else if ((threads) <= 256) HC_LAUNCH_ONE(K, 256, grid, threads, smem, stream, __VA_ARGS__); \
+    else if ((threads) <= 512) HC_LAUNCH_ONE(K, 512, grid, threads, smem, stream, __VA_ARGS__); \
+    else HC_LAUNCH_ONE(K, 1024, grid, threads, smem, stream, __VA_ARGS__);                      \
   } while (0)
 static inline int hc_grid(int M, int threads) {
   const int per_sm = max(1, 1024 / threads);
