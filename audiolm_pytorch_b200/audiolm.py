@@ -73,6 +73,37 @@ def _quantizer_ids(n, q, device):
     return torch.arange(n, device=device) % q
 
 
+class _EmbedGatherFn(torch.autograd.Function):
+    """tokens [M, d] = sum of up to two rows of the parameter tables per position (alm_embed_gather); the backward is one
+    vector-reduction scatter into fresh gradient tables (alm_embed_scatter) instead of a sort-based
+    embedding_dense_backward per table."""
+
+    @staticmethod
+    def forward(ctx, src, d, *tables):
+        flat = [t.detach().reshape(-1, d).float().contiguous() for t in tables]
+        ctx.src, ctx.d, ctx.shapes = src, d, [t.shape for t in tables]
+        return ops.embed_gather(src, flat, d)
+
+    @staticmethod
+    def backward(ctx, dout):
+        d = ctx.d
+        grads = [torch.zeros(shape, device=dout.device, dtype=torch.float32) for shape in ctx.shapes]
+        ops.embed_scatter(ctx.src, [g.view(-1, d) for g in grads], dout.contiguous().float())
+        return (None, None, *grads)
+
+
+def _src(table_id, rows):
+    """source-list entry (table_id << 24) | row for int64 row indices (rows < 0 stay -1 = no contribution)"""
+    return torch.where(rows >= 0, rows + (table_id << 24), torch.full_like(rows, -1))
+
+
+def _gather_tokens(src0, src1, tables, d):
+    """src0 / src1 int64 [b, n] source lists -> tokens fp32 [b, n, d]"""
+    b, n = src0.shape
+    src = torch.stack((src0, src1), dim=-1).to(torch.int32).reshape(b * n, 2).contiguous()
+    return _EmbedGatherFn.apply(src, d, *tables).view(b, n, d)
+
+
 class _TokenTransformer(nn.Module):
     """Shared scaffolding: conditioning guard, text projection parameter (kept for checkpoint
     compatibility), checkpoint loading, classifier-free-guidance wrapper."""
@@ -132,8 +163,11 @@ class SemanticTransformer(_TokenTransformer):
         self._no_text(text, text_embeds)
         if return_loss:
             ids = ids[:, :-1]
-        tokens = get_embeds(self.semantic_embedding, ids)
-        tokens = torch.cat((self.start_token.expand(ids.shape[0], 1, -1), tokens), dim=1)
+        # [start token | embedding rows] in one gather launch (padding ids contribute nothing, audiolm_pytorch.py:166-187)
+        zero = torch.zeros((ids.shape[0], 1), dtype=torch.long, device=ids.device)  # (ids may have 0 columns)
+        src0 = torch.cat((_src(0, zero), _src(1, ids.long())), dim=1)
+        tokens = _gather_tokens(src0, src0.new_full(src0.shape, -1), [self.start_token, self.semantic_embedding.weight],
+                                self.start_token.shape[-1])
         if exists(self_attn_mask):
             self_attn_mask = F.pad(self_attn_mask, (1, 0), value=True)
         tokens, kv = self.transformer(tokens, self_attn_mask=self_attn_mask, kv_cache=kv_cache, return_kv_cache=True) \
@@ -201,13 +235,18 @@ class CoarseTransformer(_TokenTransformer):
         semantic_token_ids = semantic_token_ids.reshape(b, -1)
         nc = coarse_token_ids.shape[-1]
         qid = _quantizer_ids(nc, q, dev)
+        S = semantic_token_ids.shape[1]
         # the reference offsets ids by codebook_size (not codebook_size+1) per quantizer (:896-899)
-        coarse = self.coarse_embedding(coarse_token_ids + qid * self.codebook_size)
-        coarse = coarse + _tile_rows(self.coarse_quantize_embedding.weight, nc)
-        sem = get_embeds(self.semantic_embedding, semantic_token_ids)
-        S = sem.shape[1]
-        tokens = torch.cat((self.semantic_start_token.expand(b, 1, -1), sem,
-                            self.coarse_start_token.expand(b, 1, -1), coarse), dim=1)
+        # [semantic start | semantic rows | coarse start | coarse rows + quantizer rows] in one gather launch
+        zero = torch.zeros((b, 1), dtype=torch.long, device=dev)
+        none = torch.full((b, 1), -1, dtype=torch.long, device=dev)
+        src0 = torch.cat((_src(0, zero), _src(1, semantic_token_ids), _src(2, zero),
+                          _src(3, coarse_token_ids + qid * self.codebook_size)), dim=1)
+        src1 = torch.cat((none.expand(b, S + 2), _src(4, qid.expand(b, nc))), dim=1)
+        tokens = _gather_tokens(src0, src1, [self.semantic_start_token, self.semantic_embedding.weight,
+                                             self.coarse_start_token, self.coarse_embedding.weight,
+                                             self.coarse_quantize_embedding.weight],
+                                self.semantic_start_token.shape[-1])
         # relative position bias, except between the semantic and the coarse segment where one learned scalar
         # per head is used so cross attention is not dominated by relative positions (:920-936)
         attn_bias = None
@@ -320,12 +359,15 @@ class FineTransformer(_TokenTransformer):
         self_attn_mask = keep if self_attn_mask is None else (self_attn_mask & keep)
         qc, qf = self.num_coarse_quantizers, self.num_fine_quantizers
         cq, fq = _quantizer_ids(n, qc, dev), _quantizer_ids(nf, qf, dev)
-        coarse = self.coarse_embedding(coarse_token_ids + cq * self.codebook_size) + \
-            _tile_rows(self.coarse_quantize_embedding.weight, n)
-        fine = self.fine_embedding(fine_token_ids + fq * self.codebook_size) + \
-            _tile_rows(self.fine_quantize_embedding.weight, nf)
-        tokens = torch.cat((self.coarse_start_token.expand(b, 1, -1), coarse,
-                            self.fine_start_token.expand(b, 1, -1), fine), dim=1)
+        zero = torch.zeros((b, 1), dtype=torch.long, device=dev)
+        none = torch.full((b, 1), -1, dtype=torch.long, device=dev)
+        src0 = torch.cat((_src(0, zero), _src(1, coarse_token_ids + cq * self.codebook_size), _src(2, zero),
+                          _src(3, fine_token_ids + fq * self.codebook_size)), dim=1)
+        src1 = torch.cat((none, _src(4, cq.expand(b, n)), none, _src(5, fq.expand(b, nf))), dim=1)
+        tokens = _gather_tokens(src0, src1, [self.coarse_start_token, self.coarse_embedding.weight,
+                                             self.fine_start_token, self.fine_embedding.weight,
+                                             self.coarse_quantize_embedding.weight,
+                                             self.fine_quantize_embedding.weight], self.coarse_start_token.shape[-1])
         attn_bias = None
         if exists(self.pos_bias_mlp):
             idx, mlp_in = self._pos_bias_index(n, nf, dev)

@@ -119,6 +119,34 @@ def _check_bias(bias, heads, n_q, n_k):
     return bias.stride(0), bias.stride(1)
 
 
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def embed_gather(src, tables, d):
+    """src int32 [M, 2] ((table_id << 24) | row, -1 = none), tables: list of fp32 [rows_k, d] -> fp32 [M, d]"""
+    _check_cuda(src, *tables)
+    assert src.dtype == torch.int32 and src.is_contiguous() and src.shape[1] == 2
+    assert all(t.dtype == f32 and t.is_contiguous() and t.shape[-1] == d for t in tables)
+    M = src.shape[0]
+    out = torch.empty(M, d, device=src.device, dtype=f32)
+    import ctypes
+    _lib.call("alm_embed_gather", ctypes.cast(_ptr_array(tables), ctypes.c_void_p), len(tables), src, out, M, d)
+    return out
+
+
+def embed_scatter(src, grad_tables, dout):
+    """backward of embed_gather: grad_tables[id][row] += dout[m] (grad tables zeroed by the caller)"""
+    _check_cuda(src, dout, *grad_tables)
+    M, d = dout.shape
+    assert dout.dtype == f32 and dout.is_contiguous()
+    import ctypes
+    _lib.call("alm_embed_scatter", ctypes.cast(_ptr_array(grad_tables), ctypes.c_void_p), len(grad_tables), src, dout,
+              M, d)
+
+
 class PackedKeyMask:
     """key mask in the bit layout the attention kernels read (alm_pack_key_mask): uint32 [b, 4 * ceil(n_k / 128)]"""
 

@@ -57,6 +57,17 @@ int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const v
 
 /* ---- multi-query attention (tcgen05 + TMA, flash-style online softmax) ----------------------- */
 /*
+ * Token embeddings of the three transformers (audiolm_pytorch.py:686-699, 896-918, 1188-1223): every position is the
+ * sum of up to two rows of a handful of fp32 parameter tables [rows_k, d] (start token, nn.Embedding rows, quantizer
+ * embedding).  tables / grad_tables: HOST array of n_tables <= 8 device pointers (16-B aligned); src: device int32
+ * [M, 2], each entry (table_id << 24) | row or -1.  gather: out [M, d] = sum of the rows.  scatter (its backward):
+ * grad_tables[id][row] += dout[m] with 16-byte vector reductions (the caller zeroes the grad tables).
+ */
+int alm_embed_gather(const float* const* tables, int n_tables, const int32_t* src, float* out, int M, int d,
+                     alm_stream_t stream);
+int alm_embed_scatter(float* const* grad_tables, int n_tables, const int32_t* src, const float* dout, int M, int d,
+                      alm_stream_t stream);
+/*
  * Key-padding / forgetful-causal mask in the form the attention kernels read: uint8 [b, n_k] (non-zero = attend) ->
  * uint32 bits [b, 4 * ceil(n_k / 128)], bit i of word w = key 32 w + i.  One call per forward (all layers and the
  * backward share the result); a 128-key tile then costs every CTA one 16-byte load instead of 128 byte tests per row.

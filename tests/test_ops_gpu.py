@@ -213,3 +213,37 @@ def test_axpby_cast():
     w = torch.randn(50, 2730, device=DEV)
     p = ops.cast_pad(w, 2736)
     assert torch.equal(p[:, :2730], w.to(bf16)) and (p[:, 2730:] == 0).all()
+
+
+def test_embed_gather_scatter_vs_torch():
+    """alm_embed_gather / alm_embed_scatter vs index_select + index_add on the source-list encoding"""
+    from audiolm_pytorch_b200 import ops
+
+    torch.manual_seed(3)
+    d = 256
+    tables = [torch.randn(r, d, device=DEV) for r in (1, 501, 1, 3075, 3)]
+    M = 4000
+    tid0 = torch.randint(0, 4, (M,), device=DEV)
+    rows0 = torch.stack([torch.randint(0, tables[t].shape[0], (1,), device=DEV)[0] for t in tid0.tolist()])
+    src0 = (tid0 << 24) | rows0
+    src0[::37] = -1                                       # padding positions
+    src1 = torch.where(torch.rand(M, device=DEV) < 0.6, (4 << 24) | torch.randint(0, 3, (M,), device=DEV),
+                       torch.full((M,), -1, device=DEV))
+    src = torch.stack((src0, src1), -1).to(torch.int32).contiguous()
+    out = ops.embed_gather(src, tables, d)
+    ref = torch.zeros(M, d, device=DEV)
+    for col in (src0, src1):
+        ok = col >= 0
+        for t in range(5):
+            sel = ok & ((col >> 24) == t)
+            ref[sel] += tables[t][(col[sel] & 0xFFFFFF)]
+    assert torch.equal(out, ref) or (out - ref).abs().max().item() < 1e-6
+    dout = torch.randn(M, d, device=DEV)
+    grads = [torch.zeros_like(t) for t in tables]
+    ops.embed_scatter(src, grads, dout)
+    for t in range(5):
+        g_ref = torch.zeros_like(tables[t])
+        for col in (src0, src1):
+            sel = (col >= 0) & ((col >> 24) == t)
+            g_ref.index_add_(0, col[sel] & 0xFFFFFF, dout[sel])
+        assert rel_err(grads[t], g_ref) < 1e-5
