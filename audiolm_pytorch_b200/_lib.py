@@ -43,6 +43,7 @@ SIGNATURES: dict[str, list] = {
     "alm_ce_fwd_bwd": [P, L, P, L, P, P, L, P, P, I, I, I, P],
     "alm_axpby_bf16": [P, L, F, P, L, F, P, L, L, I, P],
     "alm_cast_pad_bf16": [P, L, P, L, L, I, I, P],
+    "alm_cast_pad_multi": [P, I, P],
     "alm_scale_by_scalar_bf16": [P, P, L, P],
     "alm_topk_gumbel_sample": [P, L, P, L, P, I, I, I, F, P],
     "alm_resid_ln_fwd": [P, P, P, P, P, P, P, I, I, P],

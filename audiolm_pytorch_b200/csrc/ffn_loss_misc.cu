@@ -618,6 +618,33 @@ extern "C" int alm_cast_pad_bf16(const float* src, int64_t lds, void* dst, int64
   return ALM_OK;
 }
 
+// every weight of a model in ONE launch: desc[i] = {src, dst, rows, cols, cols_pad, lds, ldd} (int64 each), blockIdx.y = i
+namespace alm {
+__global__ void __launch_bounds__(256) cast_pad_multi_kernel(const long long* __restrict__ desc) {
+  const long long* d = desc + 7 * (long long)blockIdx.y;
+  const float* src = reinterpret_cast<const float*>(d[0]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d[1]);
+  const long long rows = d[2], cols = d[3], cols_pad = d[4], lds = d[5], ldd = d[6];
+  const long long pairs = cols_pad / 2;  // cols_pad is even (multiple of 8)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * pairs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / pairs, c = (i - r * pairs) * 2;
+    const float a = c < cols ? src[r * lds + c] : 0.f;
+    const float b = c + 1 < cols ? src[r * lds + c + 1] : 0.f;
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * ldd + c) = __floats2bfloat162_rn(a, b);
+  }
+}
+}  // namespace alm
+
+extern "C" int alm_cast_pad_multi(const int64_t* desc_dev, int n, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(desc_dev && n > 0 && n <= 65535, ALM_ERR_ARG);
+  alm::cast_pad_multi_kernel<<<dim3(96, n), 256, 0, stream>>>(reinterpret_cast<const long long*>(desc_dev));
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}
+
 extern "C" int alm_scale_by_scalar_bf16(void* x, const float* s, int64_t n, alm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(n > 0 && s, ALM_ERR_ARG);

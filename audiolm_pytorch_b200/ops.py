@@ -437,6 +437,13 @@ def cast_pad(src, cols_pad=None, out=None):
     return out
 
 
+def cast_pad_multi(desc):
+    """desc: device int64 [n, 7] rows {src ptr, dst ptr, rows, cols, cols_pad, lds, ldd}: all casts in one launch"""
+    _check_cuda(desc)
+    assert desc.dtype == torch.int64 and desc.is_contiguous() and desc.shape[1] == 7
+    _lib.call("alm_cast_pad_multi", desc, desc.shape[0])
+
+
 def scale_by_scalar(x, s):
     _lib.call("alm_scale_by_scalar_bf16", x, s, x.numel())
     return x

@@ -331,7 +331,52 @@ class Transformer(nn.Module):
 
     PER_LAYER = 2 * len(HC_KEYS) + 4 + 4
 
+    def _pack_all(self):
+        """re-pack the bf16 operand copies of EVERY Linear of the stack in one launch (alm_cast_pad_multi) whenever a
+        weight changed (optimizer step) or the cache was invalidated; the destination buffers are persistent, so captured
+        decode graphs keep pointing at live memory."""
+        pk = self._packed
+        items = []  # (cache key, param, source rows view, destination view)
+        bufs = self.__dict__.setdefault("_pack_bufs", {})
+
+        def buf(key, rows, cols, dev):
+            b = bufs.get(key)
+            if b is None or b.shape != (rows, cols) or b.device != dev:
+                with torch.inference_mode(False), torch.no_grad():
+                    b = bufs[key] = torch.zeros(rows, cols, device=dev, dtype=bf16)
+            return b
+
+        for i, (attn_w, _, ff_w) in enumerate(self.layers):
+            a, f = attn_w.branch, ff_w.branch
+            for name, w in (("q", a.to_q.weight), ("kv", a.to_kv.weight), ("o", a.to_out[0].weight),
+                            ("w2", getattr(f, "5").weight)):
+                dst = buf((i, name), w.shape[0], _pad8(w.shape[1]), w.device)
+                items.append(((i, name), w, w.detach(), dst, dst))
+            w1 = getattr(f, "1").weight
+            ip = _pad8(f.inner)
+            dst = buf((i, "w1"), 2 * ip, w1.shape[1], w1.device)   # a rows then gate rows, each block padded to ip rows
+            items.append(((i, "w1"), w1, w1.detach()[:f.inner], dst[:f.inner], dst))
+            items.append(((i, "w1"), w1, w1.detach()[f.inner:], dst[ip:ip + f.inner], dst))
+        ver_all = tuple((w.data_ptr(), w._version) for _, w, _, _, _ in items)
+        if self.__dict__.get("_pack_ver") == (ver_all, pk.generation):
+            return
+        sig = tuple((src.data_ptr(), d.data_ptr()) for _, _, src, d, _ in items)
+        if self.__dict__.get("_pack_sig") != sig:
+            rows = [[src.data_ptr(), d.data_ptr(), src.shape[0], src.shape[1], d.shape[1], src.stride(0), d.stride(0)]
+                    for _, _, src, d, _ in items]
+            with torch.inference_mode(False):
+                self.__dict__["_pack_desc"] = torch.tensor(rows, dtype=torch.int64, device=items[0][1].device)
+            self.__dict__["_pack_sig"] = sig
+        ops.cast_pad_multi(self.__dict__["_pack_desc"])
+        for key, w, _, _, full in items:
+            pk._cache[key] = (((w.data_ptr(), w._version),), full)
+        self.__dict__["_pack_ver"] = (ver_all, pk.generation)
+
     def _weights(self, i):
+        wq_ = self.layers[i][0].branch.to_q.weight
+        hit = self._packed._cache.get((i, "q"))
+        if wq_.is_cuda and (hit is None or hit[0] != ((wq_.data_ptr(), wq_._version),)):
+            self._pack_all()   # stale (optimizer step / invalidate): refresh every layer's copies in one launch
         attn_hc, _, ff_hc = self.layers[i]
         a, f = attn_hc.branch, ff_hc.branch
         pk = self._packed

@@ -221,6 +221,11 @@ int alm_axpby_bf16(const void* x, int64_t ldx, float alpha, const void* y, int64
 /* fp32 master weights -> zero-padded bf16 GEMM operands (what autocast does at every Linear) */
 int alm_cast_pad_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, int cols_pad,
                       alm_stream_t stream);
+/*
+ * The same cast for MANY tensors in one launch (every Linear of a model after an optimizer step; what bf16 autocast does
+ * per Linear per forward): desc_dev = device int64 [n][7] = {src ptr, dst ptr, rows, cols, cols_pad (even), lds, ldd}.
+ */
+int alm_cast_pad_multi(const int64_t* desc_dev, int n, alm_stream_t stream);
 int alm_scale_by_scalar_bf16(void* x, const float* s, int64_t n, alm_stream_t stream);
 
 /* ---- SoundStream codec (fp32) ---------------------------------------------------------------- */
