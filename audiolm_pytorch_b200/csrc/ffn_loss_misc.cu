@@ -69,23 +69,6 @@ __device__ __forceinline__ void block_sum_nt(float (&v)[N], float* buf /*[N][NT/
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
 
-// Phi(x) = 0.5 (1 + erf(x / sqrt2)) and x * phi(x) for the erf GELU (audiolm_pytorch.py:246-249: F.gelu default)
-// with ONE exponential: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, two orders below the bf16 outputs'
-// rounding), whose exp(-(x/sqrt2)^2) is also the Gaussian density.  ~14 instructions vs ~35 for erff + __expf.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& xpdf) {
-  const float ax = fabsf(x) * 0.7071067811865476f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-  float e;
-  const float arg = -0.7213475204444817f * x * x;  // -x^2/2 * log2(e)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  const float half_tail = 0.5f * p * t * e;          // 0.5 * (1 - erf(|x|/sqrt2))
-  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
-  xpdf = 0.3989422804014327f * x * e;
-}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -391,26 +374,64 @@ topk_gumbel_kernel(const float* __restrict__ logits, long long ldl, const float*
   __shared__ float red_v[SMP_THREADS / 32];
   __shared__ int red_i[SMP_THREADS / 32];
   __shared__ int cnt_gt;
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sel_prefix, sel_remaining;
   const int r = blockIdx.x;
   const float* row = logits + (size_t)r * ldl;
-  int P = 1;
-  while (P < V) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += SMP_THREADS) keys[i] = i < V ? row[i] : -INFINITY;
-  if (threadIdx.x == 0) cnt_gt = 0;
-  __syncthreads();
-  // bitonic sort, descending
-  for (int size = 2; size <= P; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < P / 2; i += SMP_THREADS) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const float a = keys[lo], b = keys[hi];
-        if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
+  float thr;
+  if (V <= SMP_MAXV) {
+    int P = 1;
+    while (P < V) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += SMP_THREADS) keys[i] = i < V ? row[i] : -INFINITY;
+    if (threadIdx.x == 0) cnt_gt = 0;
+    __syncthreads();
+    // bitonic sort, descending
+    for (int size = 2; size <= P; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < P / 2; i += SMP_THREADS) {
+          const int lo = 2 * i - (i & (stride - 1));
+          const int hi = lo + stride;
+          const bool desc = ((lo & size) == 0);
+          const float a = keys[lo], b = keys[hi];
+          if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
+        }
+        __syncthreads();
+      }
+    thr = keys[min(k, V) - 1];
+  } else {
+    // large vocabularies: k-th largest by a 4-pass radix select over the order-preserving integer image of the floats
+    auto okey = [](float f) -> unsigned {
+      const unsigned u = __float_as_uint(f);
+      return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    };
+    if (threadIdx.x == 0) { cnt_gt = 0; sel_prefix = 0; sel_remaining = (unsigned)min(k, V); }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += SMP_THREADS) hist[i] = 0;
+      __syncthreads();
+      const unsigned prefix = sel_prefix;
+      const unsigned pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int c = threadIdx.x; c < V; c += SMP_THREADS) {
+        const unsigned kk = okey(row[c]);
+        if ((kk & pmask) == prefix) atomicAdd(&hist[(kk >> shift) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned rem = sel_remaining;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (hist[b] >= rem) break;
+          rem -= hist[b];
+        }
+        sel_prefix = prefix | ((unsigned)b << shift);
+        sel_remaining = rem;
       }
       __syncthreads();
     }
-  const float thr = keys[min(k, V) - 1];
+    const unsigned kt = sel_prefix;  // integer image of the k-th largest logit
+    thr = __uint_as_float((kt & 0x80000000u) ? (kt & 0x7FFFFFFFu) : ~kt);
+  }
   int local = 0;
   for (int c = threadIdx.x; c < V; c += SMP_THREADS) local += row[c] > thr;
   local = (int)warp_sum((float)local);
@@ -658,7 +679,6 @@ extern "C" int alm_topk_gumbel_sample(const float* logits, int64_t ldl, const fl
                                       int rows, int V, int k, float temperature, alm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ALM_REQUIRE(logits && uniform && ids && rows > 0 && V > 0 && k > 0 && temperature > 0.f, ALM_ERR_ARG);
-  ALM_REQUIRE(V <= SMP_MAXV, ALM_ERR_UNSUPPORTED);
   topk_gumbel_kernel<<<rows, SMP_THREADS, 0, stream>>>(logits, ldl, uniform, ldu, reinterpret_cast<long long*>(ids), V,
                                                        k, 1.f / temperature);
   ALM_CHECK_LAUNCH();

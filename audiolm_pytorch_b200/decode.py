@@ -25,6 +25,11 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 
 
+# one persistent kernel per token (csrc/decode_step.cu) instead of ~11 launches per layer; off = the multi-kernel step
+# (kept: it is the independent implementation the fused step is tested against, and it takes more than 4 rows)
+FUSED_STACK_STEP = True
+
+
 def engine_supported(tr: Transformer) -> bool:
     """the static-cache step is built for the 4-stream hyper-connection stack on the flash path"""
     return tr.num_residual_streams == 4 and tr.rel_pos_bias is None
@@ -43,6 +48,52 @@ class StackDecoder:
         # key mask (1 = attend): a STATIC buffer so that captured graphs keep pointing at it; all ones by default
         self.mask = torch.ones(batch, max_len, device=dev, dtype=torch.uint8)
         self.host_len = 0  # host mirror of `len` (graph replays advance it too): a full cache is an error, not a drop
+        self._fused = None  # (signature, pointer table, scratch, out) of the one-kernel step
+
+    def _fused_state(self):
+        """device pointer table + per-CTA regrouped operand copies of alm_decode_stack_step; rebuilt only when a
+        parameter / packed copy changed (never during graph capture: the warm-up steps of GraphedStep build it)."""
+        tr = self.tr
+        Ws = [tr._weights(i) for i in range(tr.depth)]   # refreshes the packed bf16 copies if a weight moved
+        small = []
+        for attn_hc, _, ff_hc in tr.layers:
+            f = ff_hc.branch
+            small.append([*attn_hc.kernel_params().values(), attn_hc.branch.norm.gamma,
+                          *ff_hc.kernel_params().values(), getattr(f, "0").gamma, getattr(f, "3").gamma])
+        sig = (tuple(t.data_ptr() for ts in small for t in ts), tuple(w.data_ptr() for W in Ws for w in W.values()),
+               tr.__dict__.get("_pack_ver"), tr._packed.generation)
+        if self._fused is None or self._fused[0] != sig:
+            dev = self.kc.device
+            f0 = tr.layers[0][2].branch
+            G = ops.decode_stack_grid()
+            with torch.inference_mode(False), torch.no_grad():
+                rows, keep = [], []
+                for i, W in enumerate(Ws):
+                    ts = small[i]
+                    for t in ts:
+                        assert t.dtype == f32 and t.is_contiguous()
+                    wa = ops.regroup_rows(torch.cat((W["wq"], W["wkv"]), dim=0), G)
+                    wc, wd, we = (ops.regroup_rows(W[k], G) for k in ("wo", "w1", "w2"))
+                    keep.append((wa, wc, wd, we))
+                    rows.append([t.data_ptr() for t in ts[:16]] + [wa.data_ptr(), 0, wc.data_ptr(), wd.data_ptr(),
+                                we.data_ptr(), ts[16].data_ptr(), self.kc[i].data_ptr(), self.vc[i].data_ptr()])
+                table = torch.tensor(rows, dtype=torch.int64, device=dev)
+                scratch = ops.decode_stack_scratch(self.b, tr.dim, tr.heads, f0.inner, dev)
+                out = torch.empty(self.b, tr.dim, device=dev, dtype=bf16)
+            self._fused = (sig, table, scratch, out, keep, G)
+        return self._fused
+
+    def fused_ok(self):
+        tr = self.tr
+        inner = tr.layers[0][2].branch.inner
+        return (FUSED_STACK_STEP and self.b <= ops.DECODE_STEP_MAX_ROWS and tr.dim <= 2048 and tr.heads <= 64
+                and inner <= 4096 and tr.depth <= 64)
+
+    def barrier_timeouts(self) -> int:
+        """sticky error flag of the one-kernel step (a device-wide barrier gave up waiting); 0 when healthy"""
+        if self._fused is None:
+            return 0
+        return int(self._fused[2][256:260].view(torch.int32).item())
 
     def load_cache(self, kv):
         """kv: [depth, 2, b, n, 64] as returned by Transformer(..., return_kv_cache=True)"""
@@ -65,6 +116,12 @@ class StackDecoder:
         tr = self.tr
         b, d, H = self.b, tr.dim, tr.heads
         x2 = x.reshape(b, d).to(f32).contiguous()
+        if self.fused_ok():
+            _, table, scratch, out, _, G = self._fused_state()
+            f0 = tr.layers[0][2].branch
+            ops.decode_stack_step(table, x2, out, tr.norm.gamma, self.len, self.kc, self.mask, scratch, heads=H,
+                                  inner=f0.inner, grid=G, value_residual=tr.add_value_residual)
+            return out   # (the kernel advanced self.len)
         # a few rows: every Linear is a weight-read-bound matrix-vector product (alm_gemv_bf16 over all SMs)
         mm = (lambda a, w: ops.gemv(a, w)) if b <= 8 else (lambda a, w: ops.gemm(a, w))
         hc0 = tr.layers[0][0]

@@ -282,6 +282,51 @@ def mqa_attn_decode(q, k_cache, v_cache, cache_len, *, heads, key_mask=None, sca
     return o
 
 
+DECODE_STEP_MAX_ROWS = 4
+
+
+def decode_stack_scratch(b, d, heads, inner, device):
+    """workspace of alm_decode_stack_step (barrier counter + error flag + the vectors that cross its barriers)."""
+    n = int(_lib.load().alm_decode_stack_scratch_bytes(b, d, heads, inner))
+    if n <= 0:
+        raise _lib.AlmError(f"alm_decode_stack_step does not take b={b}, d={d}, heads={heads}, inner={inner}")
+    return torch.zeros(n, device=device, dtype=torch.uint8)
+
+
+def decode_stack_grid():
+    """CTAs of the one-kernel decode step (= SMs); the engine regroups its operands for this count."""
+    return int(_lib.load().alm_decode_stack_grid())
+
+
+def regroup_rows(w, grid):
+    """[N, K] -> [grid * pc, K] with row (c * pc + l) = w[c + l * grid] (zeros past N): CTA c's rows become contiguous."""
+    N, K = w.shape
+    pc = -(-N // grid)
+    wp = torch.zeros(pc * grid, K, device=w.device, dtype=w.dtype)
+    wp[:N] = w
+    return wp.view(pc, grid, K).transpose(0, 1).contiguous().view(grid * pc, K)
+
+
+def decode_stack_step(table, x, out, final_gamma, cache_len, k_cache, key_mask, scratch, *, heads, inner, grid,
+                      value_residual=True, scale=None):
+    """the whole hyper-connection stack for ONE new token per sequence in one cooperative kernel.
+    table: int64 [L, 24] device pointers (see include/alm_b200.h); x fp32 [b, d]; out bf16 [b, d];
+    k_cache: [L, b, max_len, 64] (only its strides / max_len are read here; the table holds the per-layer bases).
+    Increments cache_len on the device."""
+    _check_cuda(table, x, out, final_gamma, cache_len, key_mask, scratch)
+    L, b, max_len, dh = k_cache.shape
+    d = x.shape[1]
+    assert table.dtype == torch.int64 and table.shape == (L, 24) and table.is_contiguous()
+    assert x.dtype == f32 and x.is_contiguous() and out.dtype == bf16 and out.is_contiguous() and x.shape == (b, d)
+    assert dh == 64 and k_cache.stride(2) == 64 and cache_len.dtype == torch.int32 and final_gamma.dtype == f32
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.shape[0] == b and key_mask.shape[1] >= max_len
+    _lib.call("alm_decode_stack_step", table, L, x, out, final_gamma, cache_len, max_len, k_cache.stride(1), key_mask,
+              0 if key_mask is None else key_mask.stride(0), scratch, scratch.numel(), b, d, heads, inner,
+              int(bool(value_residual)), float(64 ** -0.5 if scale is None else scale), grid)
+    return out
+
+
 def bias_gather_fwd(table, idx, override, *, ld=None):
     """table [P, H] fp32, idx [n_q, n_k] int32 (-1 = override), override [H] fp32 or None -> bias [H, n_q, ld] fp32."""
     _check_cuda(table, idx, override)

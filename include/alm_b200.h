@@ -141,6 +141,32 @@ int alm_mqa_attn_decode(const void* q, int64_t ldq, const void* k_cache, const v
                         int64_t ldo, float* workspace /* [b, splits, h, 66] fp32 when splits > 1 */, int splits, int b,
                         int h, float scale, alm_stream_t stream);
 
+/* One decode step of the WHOLE 4-stream hyper-connection stack (all layers: hyper-connection pre, q / kv projections,
+ * value residual, cache append, attention over the static cache, out projection, feed-forward with GEGLU + LayerNorm,
+ * final depth connection + LayerNorm) in ONE persistent cooperative kernel with device-wide barriers: what
+ * Transformer.forward does for one new token under kv_cache (audiolm_pytorch.py:446-560 as driven by generate,
+ * :1406-1511, 1608-1740, 1896-2039).  rows b <= 4.
+ *   layer_table : device array [n_layers][24] of device pointers, per layer
+ *       0..7   attention-branch hyper-connection: norm gamma [d], dynamic_alpha_fn [d,5], dynamic_beta_fn [d],
+ *              static_alpha [4,5], static_beta [4], dynamic_alpha_scale [1], dynamic_beta_scale [1], branch LayerNorm gamma [d]
+ *       8..15  the same eight for the feed-forward branch
+ *       16, 18, 19, 20  bf16 operands REGROUPED per CTA (G = alm_decode_stack_grid() CTAs, pc = ceil(N / G)): row
+ *              (c * pc + l) of the [G * pc, K] copy is row (c + l * G) of the [N, K] operand, zero rows past N; operands:
+ *              [to_q ; to_kv] [h*64 + 128, d], to_out [d, h*64], W1 [2*pad8(inner), d] (value rows then gate rows, each
+ *              block padded to pad8(inner)), W2 [d, pad8(inner)] (zero-padded columns).  17: unused.
+ *       21     the inner LayerNorm gamma [inner] (fp32)
+ *       22..23 k_cache, v_cache of the layer: bf16 [b, max_len, 64], batch stride cache_bstride
+ *   x fp32 [b, d] (embedding of the new token), out bf16 [b, d]; *len is the cache fill level: the new token is written
+ *   at position *len and *len is incremented by the kernel.  scratch: alm_decode_stack_scratch_bytes() bytes, 256-B
+ *   aligned, owned by the caller; its first word pair is {barrier counter, sticky error flag (1 = a barrier timed out)}. */
+int alm_decode_stack_grid(void);
+int64_t alm_decode_stack_scratch_bytes(int b, int d, int heads, int inner);
+int64_t alm_decode_stack_trace_offset(int b, int d, int heads, int inner); /* debugging: phase stamps of -DALM_DSTEP_TRACE builds */
+int alm_decode_stack_step(const void* layer_table, int n_layers, const float* x, void* out, const float* final_gamma,
+                          int32_t* len, int max_len, int64_t cache_bstride, const void* key_mask, int64_t mask_bstride,
+                          void* scratch, int64_t scratch_bytes, int b, int d, int heads, int inner, int value_residual,
+                          float scale, int grid_ctas /* = alm_decode_stack_grid() */, alm_stream_t stream);
+
 /* ---- Hyper-Connections residual streams fused with the pre-LayerNorm (HBM-bound) ---------------- */
 /*
  * Internal layout: residual streams R [M, S=4, d] bf16, M = batch*seq.  One call per branch does

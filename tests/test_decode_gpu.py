@@ -173,3 +173,48 @@ def test_coarse_and_fine_generate_on_engine_match_slow_path_statistics():
     slow = fw.generate(coarse_token_ids=coarse.view(2, 4, 3), temperature=1e-4, filter_thres=0.0, use_kv_cache=False)
     assert fast.shape == slow.shape == (2, 4, 5)
     assert (fast == slow).float().mean().item() > 0.9
+
+
+@pytest.mark.parametrize("b,d,heads,depth,n0", [(1, 1024, 8, 2, 300), (3, 256, 4, 3, 37), (4, 1024, 8, 1, 2040),
+                                               (2, 64, 2, 2, 0)])
+def test_fused_stack_step_matches_multi_kernel_step(b, d, heads, depth, n0):
+    """alm_decode_stack_step (one cooperative kernel per token) vs the multi-kernel step it replaces: same outputs,
+    same rows appended to the cache, same fill level; its device-wide barriers never time out."""
+    from audiolm_pytorch_b200 import decode
+    from audiolm_pytorch_b200.transformer import Transformer
+
+    torch.manual_seed(d + b)
+    tr = Transformer(dim=d, depth=depth, heads=heads, flash_attn=True).to(DEV).eval()
+    with torch.no_grad():
+        for name, p in tr.named_parameters():
+            if "dynamic_alpha_fn" in name or "dynamic_beta_fn" in name:
+                p.normal_(0, 0.05)
+            elif name.endswith("_scale"):
+                p.fill_(0.3)
+            elif "gamma" in name:
+                p.add_(torch.randn_like(p) * 0.1)
+    max_len = 2048
+    kv = torch.randn(depth, 2, b, n0, 64, device=DEV)
+    mask = torch.rand(b, n0, device=DEV) > 0.2
+    if n0:
+        mask[:, 0] = True
+    xs = torch.randn(3, b, d, device=DEV)
+    res = []
+    for fused in (False, True):
+        decode.FUSED_STACK_STEP = fused
+        try:
+            dec = decode.StackDecoder(tr, b, max_len)
+            assert dec.fused_ok() == fused
+            dec.load_cache(kv)
+            dec.set_key_mask(mask)
+            outs = [dec.step(xs[t]).clone() for t in range(3)]
+            torch.cuda.synchronize()
+            assert int(dec.len.item()) == n0 + 3
+            assert dec.barrier_timeouts() == 0
+            res.append((torch.stack(outs), dec.kc[:, :, n0:n0 + 3].clone(), dec.vc[:, :, n0:n0 + 3].clone()))
+        finally:
+            decode.FUSED_STACK_STEP = True
+    (o0, k0, v0), (o1, k1, v1) = res
+    assert torch.isfinite(o1.float()).all()
+    assert rms_rel(o1, o0) < 2e-2, rms_rel(o1, o0)
+    assert rms_rel(k1, k0) < 2e-2 and rms_rel(v1, v0) < 2e-2, (rms_rel(k1, k0), rms_rel(v1, v0))

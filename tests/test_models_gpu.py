@@ -181,6 +181,26 @@ def test_fused_sampler_kernel_bit_exact():
         assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize("V,ties", [(2049, False), (4097, False), (32000, False), (5000, True)])
+def test_fused_sampler_large_vocab(V, ties):
+    """V > 2048 takes the radix-select threshold path of alm_topk_gumbel_sample; ties at the threshold keep the lowest
+    indices (stable descending sort), mixed-sign logits and -inf entries included."""
+    from audiolm_pytorch_b200 import ops
+
+    torch.manual_seed(V)
+    logits = torch.randn(16, V, device=DEV) * 4
+    if ties:
+        logits = (logits * 2).round() / 2
+    logits[:, 7] = float("-inf")
+    u = torch.rand(16, V, device=DEV)
+    k = max(int(0.1 * V), 1)
+    order = torch.sort(logits, dim=-1, descending=True, stable=True).indices[:, :k]
+    filt = torch.full_like(logits, float("-inf")).scatter_(1, order, logits.gather(1, order))
+    ref = (filt / 0.9 + (-torch.log(-torch.log(u + 1e-20) + 1e-20))).argmax(-1)
+    got = ops.topk_gumbel_sample(logits, u, k=k, temperature=0.9)
+    assert torch.equal(got, ref)
+
+
 def test_generate_paths_end_to_end():
     """Semantic/Coarse/Fine .generate() with KV cache + codec decode (AudioLM.forward plumbing, tiny models).
     Also: KV-cache generation == no-cache generation under the same noise (teacher-forcing free check)."""
