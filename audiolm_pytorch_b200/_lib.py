@@ -30,6 +30,8 @@ SIGNATURES: dict[str, list] = {
     "alm_attn_delta": [P, L, P, L, P, L, I, I, I, P],
     "alm_kv_append": [P, L, P, P, L, P, I, I, P],
     "alm_gemv_bf16": [P, L, P, L, P, I, L, P, I, I, I, P],
+    "alm_gemm_head_ce": [P, L, P, L, P, P, L, I, P, P, P, P, P, P, L, I, I, I, P],
+    "alm_ce_finish": [P, I, P, P, L, P, P, I, P],
     "alm_decode_stack_step": [P, I, P, P, P, P, I, L, P, L, P, L, I, I, I, I, I, F, I, P],
     "alm_mqa_attn_decode": [P, L, P, P, L, P, I, P, L, P, L, P, I, I, I, F, P],
     "alm_bias_gather_fwd": [P, P, P, P, I, I, I, L, P],
@@ -90,6 +92,8 @@ def load() -> C.CDLL:
     lib.alm_reset_launch_count.restype = None
     lib.alm_decode_stack_scratch_bytes.restype = L
     lib.alm_decode_stack_scratch_bytes.argtypes = [I, I, I, I]
+    lib.alm_gemm_head_ce_tiles.restype = I
+    lib.alm_gemm_head_ce_tiles.argtypes = [I]
     lib.alm_decode_stack_grid.restype = I
     lib.alm_decode_stack_grid.argtypes = []
     lib.alm_decode_stack_trace_offset.restype = L

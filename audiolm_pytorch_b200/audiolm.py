@@ -14,7 +14,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .heads import (HeadCache, cross_entropy, generate_mask_with_prob, gumbel_sample, mask_out_after_eos_id, top_k)
+from . import heads as _heads_mod
+from .heads import (HeadCache, LazyLogits, cross_entropy, generate_mask_with_prob, gumbel_sample, mask_out_after_eos_id, top_k)
 from . import ops
 from .decode import StackDecoder, TokenDecoder, engine_supported
 from .rel_pos import gather_bias, mlp_table
@@ -104,9 +105,26 @@ def _gather_tokens(src0, src1, tables, d):
     return _EmbedGatherFn.apply(src, d, *tables).view(b, n, d)
 
 
+class _deferred_heads:
+    """while active (a wrapper computing its loss), the transformer returns heads.LazyLogits instead of logits tensors,
+    so that cross_entropy() can run the fused head + CE kernels; the public forward signatures stay the reference's."""
+
+    def __init__(self, transformer, on):
+        self.tr, self.on = transformer, bool(on) and _heads_mod.FUSED_HEAD_CE
+
+    def __enter__(self):
+        self.tr._defer_heads = self.on
+
+    def __exit__(self, *exc):
+        self.tr._defer_heads = False
+        return False
+
+
 class _TokenTransformer(nn.Module):
     """Shared scaffolding: conditioning guard, text projection parameter (kept for checkpoint
     compatibility), checkpoint loading, classifier-free-guidance wrapper."""
+
+    _defer_heads = False   # set by _deferred_heads around a wrapper's loss forward
 
     def _init_common(self, dim, t5_name, cond_dim, has_condition, audio_text_condition, cond_drop_prob):
         if has_condition or audio_text_condition:
@@ -173,8 +191,11 @@ class SemanticTransformer(_TokenTransformer):
         tokens, kv = self.transformer(tokens, self_attn_mask=self_attn_mask, kv_cache=kv_cache, return_kv_cache=True) \
             if (return_kv_cache or exists(kv_cache)) else (self.transformer(tokens, self_attn_mask=self_attn_mask), None)
         b, n, d = tokens.shape
-        logits = self._heads.linear(tokens.reshape(-1, d), self.to_logits.weight, self.to_logits.bias, "sem")
-        logits = logits.view(b, n, -1)
+        if self._defer_heads:   # the wrapper's loss path: head + cross entropy run fused, no logits tensor
+            logits = LazyLogits(self._heads, tokens, self.to_logits.weight, self.to_logits.bias, "sem", False)
+        else:
+            logits = self._heads.linear(tokens.reshape(-1, d), self.to_logits.weight, self.to_logits.bias, "sem")
+            logits = logits.view(b, n, -1)
         return (logits, kv) if return_kv_cache else logits
 
 
@@ -263,6 +284,12 @@ class CoarseTransformer(_TokenTransformer):
         new_embed_cache = tokens
         pred_sem, pred_coarse = tokens[:, :S], tokens[:, S + 1:]
         sem_logits = None
+        if self._defer_heads:   # the wrapper's loss path: heads + cross entropy run fused, no logits tensors
+            if not return_only_coarse_logits and exists(self.to_semantic_logits):
+                sem_logits = LazyLogits(self._heads, pred_sem, self.to_semantic_logits.weight,
+                                        self.to_semantic_logits.bias, "sem", False)
+            logits = (sem_logits, LazyLogits(self._heads, pred_coarse, self.coarse_logit_weights, None, "coarse", True))
+            return (logits, (new_kv, new_embed_cache)) if return_cache else logits
         if not return_only_coarse_logits and exists(self.to_semantic_logits):
             d = pred_sem.shape[-1]
             sem_logits = self._heads.linear(pred_sem.reshape(-1, d), self.to_semantic_logits.weight,
@@ -383,6 +410,11 @@ class FineTransformer(_TokenTransformer):
         new_embed_cache = tokens
         pred_coarse, pred_fine = tokens[:, :n], tokens[:, n + 1:]
         coarse_logits = None
+        if self._defer_heads:   # the wrapper's loss path: heads + cross entropy run fused, no logits tensors
+            if not return_only_fine_logits and exists(self.coarse_logit_weights):
+                coarse_logits = LazyLogits(self._heads, pred_coarse, self.coarse_logit_weights, None, "coarse", True)
+            logits = (coarse_logits, LazyLogits(self._heads, pred_fine, self.fine_logit_weights, None, "fine", True))
+            return (logits, (new_kv, new_embed_cache)) if return_cache else logits
         if not return_only_fine_logits and exists(self.coarse_logit_weights):
             coarse_logits = self._heads.grouped(pred_coarse, self.coarse_logit_weights, "coarse")
         fine_logits = self._heads.grouped(pred_fine, self.fine_logit_weights, "fine")
@@ -524,7 +556,8 @@ class SemanticTransformerWrapper(nn.Module):
         mask = None
         if self.mask_prob > 0.0 and self.training:
             mask = generate_mask_with_prob(input_ids.shape, self.mask_prob, input_ids.device)
-        logits = self.transformer(ids=input_ids, self_attn_mask=mask, **kwargs)
+        with _deferred_heads(self.transformer, return_loss):
+            logits = self.transformer(ids=input_ids, self_attn_mask=mask, **kwargs)
         if not return_loss:
             return logits
         return cross_entropy(logits, ids, ignore_index=self.pad_id)
@@ -698,8 +731,9 @@ class CoarseTransformerWrapper(nn.Module):
         mask = F.pad(mask, (1, coarse.shape[-1] + 1), value=True)
         if self.mask_prob > 0 and self.training:
             mask = mask & generate_mask_with_prob(mask.shape, self.mask_prob, device=mask.device)
-        sem_logits, coarse_logits = self.transformer(semantic_token_ids=sem, coarse_token_ids=coarse,
-                                                     self_attn_mask=mask, **kwargs)
+        with _deferred_heads(self.transformer, return_loss):
+            sem_logits, coarse_logits = self.transformer(semantic_token_ids=sem, coarse_token_ids=coarse,
+                                                         self_attn_mask=mask, **kwargs)
         if not return_loss:
             return sem_logits, coarse_logits
         if self.unique_consecutive:
@@ -819,8 +853,9 @@ class FineTransformerWrapper(nn.Module):
         mask = None
         if self.mask_prob > 0 and self.training:
             mask = generate_mask_with_prob((b, coarse.shape[-1] + fine.shape[-1] + 2), self.mask_prob, self.device)
-        coarse_logits, fine_logits = self.transformer(coarse_token_ids=coarse, fine_token_ids=fine,
-                                                      self_attn_mask=mask, **kwargs)
+        with _deferred_heads(self.transformer, return_loss):
+            coarse_logits, fine_logits = self.transformer(coarse_token_ids=coarse, fine_token_ids=fine,
+                                                          self_attn_mask=mask, **kwargs)
         if not return_loss:
             return coarse_logits, fine_logits
         n_fine = fine_logits.shape[1]

@@ -709,3 +709,33 @@ extern "C" int alm_resid_ln_bwd(const float* r_new, const float* gamma, const fl
   ALM_LAUNCHED(1);
   return ALM_OK;
 }
+
+// ---- fused head + cross entropy, second half of the forward: soft-max partials of alm_gemm_head_ce(mode 1) -> row LSE / loss
+namespace alm {
+__global__ void ce_finish_kernel(const float* __restrict__ part, int tiles, const float* __restrict__ lab,
+                                 const long long* __restrict__ labels, long long ignore, float* __restrict__ lse,
+                                 float* __restrict__ loss_rows, int M) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const float* pr = part + (size_t)r * tiles * 2;
+  float m = -INFINITY;
+  for (int t = 0; t < tiles; ++t) m = fmaxf(m, pr[2 * t]);
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += pr[2 * t + 1] * exp2f(pr[2 * t] - m);
+  const float l = (m + log2f(s)) * 0.6931471805599453f;
+  lse[r] = l;
+  loss_rows[r] = labels[r] == ignore ? 0.f : l - lab[r];
+}
+}  // namespace alm
+
+extern "C" int alm_ce_finish(const float* part, int tiles, const float* lab_logit, const int64_t* labels,
+                             int64_t ignore_index, float* lse, float* loss_rows, int M, alm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ALM_REQUIRE(part && lab_logit && labels && lse && loss_rows && M > 0 && tiles > 0, ALM_ERR_ARG);
+  alm::ce_finish_kernel<<<alm::ceil_div(M, 256), 256, 0, stream>>>(part, tiles, lab_logit,
+                                                                   reinterpret_cast<const long long*>(labels),
+                                                                   (long long)ignore_index, lse, loss_rows, M);
+  ALM_CHECK_LAUNCH();
+  ALM_LAUNCHED(1);
+  return ALM_OK;
+}

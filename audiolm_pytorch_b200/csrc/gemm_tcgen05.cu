@@ -20,6 +20,18 @@ struct GemmParams {
   int c_fp32, acc_mode;
   int tma_store;  // bf16 overwrite outputs: stage through smem and store with TMA (full 128-B lines)
   float alpha;
+  // fused logit head + cross entropy (CE kernel variant only; alm_gemm_head_ce):
+  //   ce_mode 1: nothing is stored; every (row, n tile) emits its soft-max partial {max, sum 2^(t - max)} of
+  //              t = logit * log2(e) into ce_part [M][n_blocks][2], and the tile that holds the label its logit into ce_lab
+  //   ce_mode 2: C (bf16) = (softmax - onehot) * (*ce_num / *ce_den), zero rows where label == ce_ignore
+  int ce_mode;
+  const long long* ce_labels;
+  long long ce_ignore;
+  float* ce_part;
+  float* ce_lab;
+  const float* ce_lse;   // natural-log LSE per row (mode 2)
+  const float* ce_num;
+  const float* ce_den;
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -37,7 +49,7 @@ struct GemmCfg {
       STAGES * (A_BYTES + B_BYTES) + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CE = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -190,6 +202,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const bool row_ok = gm < p.M;
       const long long row_off = (long long)b * p.strideC + (long long)gm * p.ldc;
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (uint32_t(q * 32) << 16);
+      // fused head + cross entropy: this thread's row state for the tile
+      float ce_m = -INFINITY, ce_s = 0.f, ce_lse2 = 0.f, ce_scale = 0.f;
+      long long ce_label = -1;
+      if constexpr (CE) {
+        if (row_ok) {
+          ce_label = p.ce_labels[gm];
+          if (p.ce_mode == 2) {
+            ce_lse2 = p.ce_lse[gm] * 1.4426950408889634f;
+            ce_scale = ce_label == p.ce_ignore ? 0.f : __ldg(p.ce_num) / __ldg(p.ce_den);
+          }
+        }
+      }
       if (p.tma_store) {
         // TMEM -> registers -> bf16 -> SW128 smem tile -> cp.async.bulk.tensor store (tails clipped by TMA)
         const bool leader = (warp == 4 && lane == 0);
@@ -255,6 +279,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j)
             if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
         }
+        if constexpr (CE) {
+          if (p.ce_mode == 1) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (nbase + j == ce_label) p.ce_lab[gm] = v[j];
+              v[j] = nbase + j < p.N ? v[j] * 1.4426950408889634f : -INFINITY;
+              cm = fmaxf(cm, v[j]);
+            }
+            const float m_new = fmaxf(ce_m, cm);   // finite: the chunk has at least one valid column
+            float add = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) add += exp2f(v[j] - m_new);
+            ce_s = ce_s * exp2f(ce_m - m_new) + add;
+            ce_m = m_new;
+            continue;   // nothing is stored in this mode
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = (exp2f(v[j] * 1.4426950408889634f - ce_lse2) - (nbase + j == ce_label ? 1.f : 0.f)) * ce_scale;
+        }
         const bool full = nbase + 32 <= p.N;
         if (p.c_fp32) {
           float* dst = reinterpret_cast<float*>(p.C) + row_off + nbase;
@@ -311,6 +356,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         }  // row_ok
       }
+      if constexpr (CE) {
+        if (p.ce_mode == 1 && row_ok) {
+          float* pp = p.ce_part + ((size_t)gm * p.n_blocks + nb) * 2;
+          pp[0] = ce_m;
+          pp[1] = ce_s;
+        }
+      }
     }
   }
 
@@ -321,11 +373,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CE = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kfn = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CE>;
   static bool attr_set = false;
   if (!attr_set) {
     ALM_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -350,13 +402,25 @@ static int pick_block_n(int N) {
 
 }  // namespace alm
 
-extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const void* B, int b_mn,
-                             int64_t ldb, int64_t strideB, void* C, int c_fp32, int64_t ldc, int64_t strideC, int M,
-                             int N, int K, int batch, float alpha, const float* bias, int acc_mode, int split_k,
-                             alm_stream_t stream_) {
+namespace alm {
+struct CeEpilogue {
+  int mode;
+  const long long* labels;
+  long long ignore;
+  float* part;
+  float* lab;
+  const float* lse;
+  const float* num;
+  const float* den;
+};
+}  // namespace alm
+
+static int gemm_common(const void* A, int a_mn, int64_t lda, int64_t strideA, const void* B, int b_mn, int64_t ldb,
+                       int64_t strideB, void* C, int c_fp32, int64_t ldc, int64_t strideC, int M, int N, int K, int batch,
+                       float alpha, const float* bias, int acc_mode, int split_k, cudaStream_t stream,
+                       const alm::CeEpilogue* ce) {
   using namespace alm;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  ALM_REQUIRE(A && B && C, ALM_ERR_ARG);
+  ALM_REQUIRE(A && B && (C || (ce && ce->mode == 1)), ALM_ERR_ARG);
   ALM_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, ALM_ERR_ARG);
   ALM_REQUIRE(acc_mode >= 0 && acc_mode <= 2 && split_k >= 1, ALM_ERR_ARG);
   ALM_REQUIRE(split_k == 1 || (acc_mode == 2 && c_fp32), ALM_ERR_ARG);
@@ -380,6 +444,17 @@ extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strid
   p.c_fp32 = c_fp32;
   p.acc_mode = acc_mode;
   p.alpha = alpha;
+  p.ce_mode = 0;
+  if (ce != nullptr) {
+    p.ce_mode = ce->mode;
+    p.ce_labels = ce->labels;
+    p.ce_ignore = ce->ignore;
+    p.ce_part = ce->part;
+    p.ce_lab = ce->lab;
+    p.ce_lse = ce->lse;
+    p.ce_num = ce->num;
+    p.ce_den = ce->den;
+  }
 
   CUtensorMap tmA, tmB;
   {
@@ -418,7 +493,7 @@ extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strid
   // bf16 overwrite outputs with 16-B aligned rows take the smem-staged TMA-store epilogue
   CUtensorMap tmC = tmA;
   p.tma_store = 0;
-  if (!c_fp32 && acc_mode == 0 && bias == nullptr && ldc % 8 == 0 && (batch == 1 || strideC % 8 == 0) &&
+  if (ce == nullptr && !c_fp32 && acc_mode == 0 && bias == nullptr && ldc % 8 == 0 && (batch == 1 || strideC % 8 == 0) &&
       (reinterpret_cast<uintptr_t>(C) & 15u) == 0) {
     uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)batch};
     uint64_t strides[3] = {2, (uint64_t)ldc * 2, batch > 1 ? (uint64_t)strideC * 2 : (uint64_t)M * ldc * 2};
@@ -428,6 +503,11 @@ extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strid
     p.tma_store = 1;
   }
 
+  if (ce != nullptr) {   // (row-major x, row-major head weight: the only layout the fused head needs)
+    if (BN == 256) return launch_gemm<256, false, false, true>(tmA, tmB, tmC, p, stream);
+    if (BN == 128) return launch_gemm<128, false, false, true>(tmA, tmB, tmC, p, stream);
+    return launch_gemm<64, false, false, true>(tmA, tmB, tmC, p, stream);
+  }
 #define ALM_GEMM_DISPATCH(BN_)                                                             \
   if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(tmA, tmB, tmC, p, stream);     \
   if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(tmA, tmB, tmC, p, stream);       \
@@ -436,4 +516,36 @@ extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strid
   if (BN == 128) { ALM_GEMM_DISPATCH(128) }
   { ALM_GEMM_DISPATCH(64) }
 #undef ALM_GEMM_DISPATCH
+}
+
+extern "C" int alm_gemm_bf16(const void* A, int a_mn, int64_t lda, int64_t strideA, const void* B, int b_mn,
+                             int64_t ldb, int64_t strideB, void* C, int c_fp32, int64_t ldc, int64_t strideC, int M,
+                             int N, int K, int batch, float alpha, const float* bias, int acc_mode, int split_k,
+                             alm_stream_t stream_) {
+  return gemm_common(A, a_mn, lda, strideA, B, b_mn, ldb, strideB, C, c_fp32, ldc, strideC, M, N, K, batch, alpha, bias,
+                     acc_mode, split_k, reinterpret_cast<cudaStream_t>(stream_), nullptr);
+}
+
+// number of n tiles of the head GEMM for a vocabulary of V (= the second dimension of `part` below)
+extern "C" int alm_gemm_head_ce_tiles(int V) { return alm::ceil_div(V, alm::pick_block_n(V)); }
+
+// Fused logit head + cross entropy (audiolm_pytorch.py:621, 798, 965-983, 1325-1361 heads; :1561-1565, 1836-1854,
+// 2119-2137 F.cross_entropy): the [M, V] fp32 logits never reach HBM.
+//   mode 1: logits = X W^T (+ bias) are reduced in the GEMM epilogue to per-(row, n tile) soft-max partials
+//           part [M, tiles, 2] = {max, sum 2^(t - max)} of t = logit * log2(e), and lab_logit [M] = logit[label];
+//           alm_ce_finish turns them into the row LSE and loss
+//   mode 2: the GEMM is recomputed and its epilogue writes d(loss)/d(logits) = (softmax - onehot) * (*scale_num /
+//           *scale_den) as bf16 [M, ldd] (rows with label == ignore_index are zero; columns >= V are not written)
+extern "C" int alm_gemm_head_ce(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                                const int64_t* labels, int64_t ignore_index, int mode, float* part, float* lab_logit,
+                                const float* lse, const float* scale_num, const float* scale_den, void* dlogits,
+                                int64_t ldd, int M, int V, int K, alm_stream_t stream_) {
+  ALM_REQUIRE(mode == 1 || mode == 2, ALM_ERR_ARG);
+  ALM_REQUIRE(labels != nullptr, ALM_ERR_ARG);
+  if (mode == 1) ALM_REQUIRE(part && lab_logit, ALM_ERR_ARG);
+  else ALM_REQUIRE(lse && scale_num && scale_den && dlogits && ldd >= V, ALM_ERR_ARG);
+  alm::CeEpilogue ce{mode, reinterpret_cast<const long long*>(labels), (long long)ignore_index, part, lab_logit, lse,
+                     scale_num, scale_den};
+  return gemm_common(X, 0, ldx, 0, W, 0, ldw, 0, dlogits, 0, ldd, 0, M, V, K, 1, 1.f, bias, 0, 1,
+                     reinterpret_cast<cudaStream_t>(stream_), &ce);
 }

@@ -21,6 +21,41 @@ def pack_head(w):
     return out
 
 
+# training losses run the head GEMM and the cross entropy as ONE fused pair of kernels (alm_gemm_head_ce): the [b, n, V]
+# fp32 logits, their strided copies and the separate CE launch disappear.  Off = logits materialised + alm_ce_fwd_bwd.
+FUSED_HEAD_CE = True
+
+
+class LazyLogits:
+    """`head(tokens)` that has NOT been computed: what the transformers hand to the wrappers' loss path
+    (`_defer_heads=True`).  cross_entropy() consumes it through the fused head + CE kernels; anything else can call
+    materialize().  `grouped`: position p uses weight[p mod Q] (per-quantizer heads)."""
+
+    def __init__(self, cache, tokens, weight, bias, key, grouped):
+        self.cache, self.tokens, self.weight, self.bias, self.key, self.grouped = cache, tokens, weight, bias, key, grouped
+        self.shape = (tokens.shape[0], tokens.shape[1], weight.shape[-2])
+
+    def materialize(self):
+        b, n, d = self.tokens.shape
+        if self.grouped:
+            return self.cache.grouped(self.tokens, self.weight, self.key)
+        return self.cache.linear(self.tokens.reshape(-1, d), self.weight, self.bias, self.key).view(b, n, -1)
+
+    def ce_sum(self, labels, ignore_index):
+        """sum over positions of the cross entropy against labels [b, n] (ignored positions contribute 0)"""
+        b, n, d = self.tokens.shape
+        if not self.grouped:
+            return self.cache.linear_ce_sum(self.tokens.reshape(-1, d), self.weight, self.bias, self.key,
+                                            labels.reshape(-1), ignore_index)
+        Q = self.weight.shape[0]
+        total = None
+        for q in range(min(Q, n)):
+            part = self.cache.linear_ce_sum(self.tokens[:, q::Q].reshape(-1, d), self.weight[q], None, (self.key, q),
+                                            labels[:, q::Q].reshape(-1), ignore_index)
+            total = part if total is None else total + part
+        return total
+
+
 class HeadCache:
     """bf16 operand copies of head weights, refreshed when the parameter version changes."""
 
@@ -35,6 +70,11 @@ class HeadCache:
         V = weight.shape[0]
         # forward uses the first V rows; backward (dgrad) uses all pad8(V) rows against the padded dlogits
         return _LinearPacked.apply(x2d, weight, bias, packed, V)
+
+    def linear_ce_sum(self, x2d, weight, bias, key, labels, ignore_index):
+        """sum_r CE(x2d[r] @ weight^T + bias, labels[r]) without materialising the logits (fused head + CE)"""
+        packed = self._pk.get(key, [weight], lambda: pack_head(weight))
+        return _HeadCESum.apply(x2d, weight, bias, packed, weight.shape[0], labels, ignore_index)
 
     @torch.no_grad()
     def linear_decode(self, x2d, weight, bias, key):
@@ -87,6 +127,36 @@ class _LinearPacked(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+class _HeadCESum(torch.autograd.Function):
+    """sum of the row cross entropies of (x @ W^T + bias): alm_gemm_head_ce mode 1 + alm_ce_finish forward, mode 2
+    (recompute, emit d logits as bf16) + the usual dgrad / wgrad GEMMs backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_packed, V, labels, ignore_index):
+        x = x.to(bf16).contiguous()
+        labels = labels.contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        lse, rows = ops.head_ce_fwd(x, w_packed[:V], b32, labels, ignore_index)
+        ctx.save_for_backward(x, lse, labels)
+        ctx.w_packed, ctx.b32 = w_packed, b32      # plain attributes: see _LinearPacked
+        ctx.V, ctx.d, ctx.ignore = V, weight.shape[1], ignore_index
+        return rows.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, lse, labels = ctx.saved_tensors
+        V, d, w_packed = ctx.V, ctx.d, ctx.w_packed
+        dlog = torch.zeros(x.shape[0], _pad8(V), device=x.device, dtype=bf16)       # zero padding columns for the dgrad
+        one = torch.ones(1, device=x.device, dtype=f32)
+        ops.head_ce_bwd(x, w_packed[:V], ctx.b32, labels, ctx.ignore, lse, g.reshape(1).to(f32).contiguous(), one, dlog)
+        dx = ops.gemm(dlog, w_packed, b_mn=True)[:, :d]
+        dw = torch.zeros(V, d, device=x.device, dtype=f32)
+        s = best_split_k(V, d, x.shape[0])
+        ops.gemm(dlog[:, :V], x[:, :d], a_mn=True, b_mn=True, out=dw, acc_mode=2 if s > 1 else 1, split_k=s)
+        db = dlog[:, :V].float().sum(0) if ctx.b32 is not None else None
+        return dx, dw, db, None, None, None, None
+
+
 class CrossEntropyFn(torch.autograd.Function):
     """mean cross entropy over rows whose label != ignore_index (fused forward + d logits kernel)."""
 
@@ -109,6 +179,9 @@ class CrossEntropyFn(torch.autograd.Function):
 
 def cross_entropy(logits, labels, ignore_index=-1):
     """F.cross_entropy(rearrange(logits, 'b n c -> b c n'), labels, ignore_index=...) for logits [b, n, c]."""
+    if isinstance(logits, LazyLogits):
+        den = (labels != ignore_index).sum().to(f32).clamp(min=1.0)
+        return logits.ce_sum(labels, ignore_index) / den
     V = logits.shape[-1]
     return CrossEntropyFn.apply(logits.reshape(-1, V), labels.reshape(-1), ignore_index)
 

@@ -282,6 +282,41 @@ def mqa_attn_decode(q, k_cache, v_cache, cache_len, *, heads, key_mask=None, sca
     return o
 
 
+def head_ce_fwd(x, w, bias, labels, ignore_index):
+    """fused logit head + cross entropy, forward: x [M, K] bf16, w [V, >=K] bf16 (+ bias [V] fp32), labels [M] int64
+    -> (lse [M] fp32, loss_rows [M] fp32 = lse - logit[label], 0 where label == ignore_index).  No logits in HBM."""
+    _check_cuda(x, w, bias, labels)
+    M, K = x.shape
+    V = w.shape[0]
+    assert x.dtype == bf16 and w.dtype == bf16 and x.stride(1) == 1 and w.stride(1) == 1 and w.shape[1] >= K
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == M
+    tiles = int(_lib.load().alm_gemm_head_ce_tiles(V))
+    part = torch.empty(M, tiles, 2, device=x.device, dtype=f32)
+    lab = torch.empty(M, device=x.device, dtype=f32)
+    lse = torch.empty(M, device=x.device, dtype=f32)
+    rows = torch.empty(M, device=x.device, dtype=f32)
+    with _timed("gemm_bf16_tcgen05", 2.0 * M * V * K):
+        _lib.call("alm_gemm_head_ce", x, x.stride(0), w, w.stride(0), bias, labels, int(ignore_index), 1, part, lab, None,
+                  None, None, None, 0, M, V, K)
+    _lib.call("alm_ce_finish", part, tiles, lab, labels, int(ignore_index), lse, rows, M)
+    return lse, rows
+
+
+def head_ce_bwd(x, w, bias, labels, ignore_index, lse, scale_num, scale_den, dlogits):
+    """fused logit head + cross entropy, backward: recomputes the logits tile by tile and writes
+    dlogits [M, >=V] bf16 = (softmax - onehot) * scale_num / scale_den (device scalars), zero rows where ignored."""
+    _check_cuda(x, w, bias, labels, lse, scale_num, scale_den, dlogits)
+    M, K = x.shape
+    V = w.shape[0]
+    assert dlogits.dtype == bf16 and dlogits.shape[0] == M and dlogits.shape[1] >= V and dlogits.stride(1) == 1
+    assert scale_num.dtype == f32 and scale_den.dtype == f32 and lse.dtype == f32
+    # the recomputation is executed work, not algorithmic work: it is timed in the GEMM class with 0 algorithmic FLOPs
+    with _timed("gemm_bf16_tcgen05", 0.0):
+        _lib.call("alm_gemm_head_ce", x, x.stride(0), w, w.stride(0), bias, labels, int(ignore_index), 2, None, None, lse,
+                  scale_num, scale_den, dlogits, dlogits.stride(0), M, V, K)
+    return dlogits
+
+
 DECODE_STEP_MAX_ROWS = 4
 
 

@@ -376,7 +376,38 @@ def config_c5(dev, window=120):
     c_ids = torch.randint(0, 1024, (1, window // 5, 3), device=dev)
     timed("fine", lambda: fine.generate(coarse_token_ids=c_ids), lambda r: window // 5 * 5)
     out["window_tokens"] = window
+    out["stack_step"] = decode_stack_step_us(dev)
     return out
+
+
+def decode_stack_step_us(dev, cache_len=600):
+    """device time of ONE decode step of the d1024 L6 stack (batch 1, 600 cached positions), replayed from a CUDA graph:
+    the one-kernel step (alm_decode_stack_step) beside the multi-kernel step it replaced."""
+    from audiolm_pytorch_b200 import decode
+    from audiolm_pytorch_b200.transformer import Transformer
+
+    tr = Transformer(dim=1024, depth=6, heads=8, flash_attn=True).to(dev).eval()
+    res = {"cache_len": cache_len}
+    for fused in (False, True):
+        decode.FUSED_STACK_STEP = fused
+        try:
+            dec = decode.StackDecoder(tr, 1, 2048)
+            dec.load_cache(torch.randn(6, 2, 1, cache_len, 64, device=dev))
+            x = torch.randn(1, 1024, device=dev)
+            y = torch.zeros(1, 1024, device=dev, dtype=torch.bfloat16)
+            g = decode.GraphedStep(lambda: y.copy_(dec.step(x)), [dec.len, y])
+            for _ in range(10):
+                g()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(100):
+                g()
+            e1.record()
+            torch.cuda.synchronize()
+            res["one_kernel_us" if fused else "multi_kernel_us"] = round(e0.elapsed_time(e1) * 10, 1)
+        finally:
+            decode.FUSED_STACK_STEP = True
+    return res
 
 
 def gemm_traffic_from_profile():

@@ -141,6 +141,24 @@ int alm_mqa_attn_decode(const void* q, int64_t ldq, const void* k_cache, const v
                         int64_t ldo, float* workspace /* [b, splits, h, 66] fp32 when splits > 1 */, int splits, int b,
                         int h, float scale, alm_stream_t stream);
 
+/* ---- fused logit head + cross entropy (the [M, V] fp32 logits never reach HBM) --------------------------------
+ * Replaces `logits = head(x)` + `F.cross_entropy(logits, labels, ignore_index=...)` of the three wrappers' loss paths
+ * (audiolm_pytorch.py:621, 798, 965-983, 1325-1361 heads; :1561-1565, 1836-1854, 2119-2137 losses).
+ *   alm_gemm_head_ce mode 1 : X [M, K] bf16 (row stride ldx) times W [V, K] bf16 (row stride ldw) (+ bias [V] fp32); the GEMM
+ *       epilogue reduces every (row, n tile) to {max, sum 2^(t - max)} of t = logit * log2(e) -> part [M, tiles, 2]
+ *       (tiles = alm_gemm_head_ce_tiles(V)) and writes logit[label] -> lab_logit [M] (rows whose label is never a column,
+ *       e.g. ignore_index = -1, are left untouched)
+ *   alm_ce_finish           : part, lab_logit -> lse [M] (natural log), loss_rows [M] = lse - logit[label] (0 when ignored)
+ *   alm_gemm_head_ce mode 2 : recomputes the GEMM and writes d loss / d logits = (softmax - onehot) * (*scale_num / *scale_den)
+ *       as bf16 [M, ldd] (zero rows where label == ignore_index; columns >= V are not written: pre-zero the padding). */
+int alm_gemm_head_ce_tiles(int V);
+int alm_gemm_head_ce(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias, const int64_t* labels,
+                     int64_t ignore_index, int mode, float* part, float* lab_logit, const float* lse,
+                     const float* scale_num, const float* scale_den, void* dlogits, int64_t ldd, int M, int V, int K,
+                     alm_stream_t stream);
+int alm_ce_finish(const float* part, int tiles, const float* lab_logit, const int64_t* labels, int64_t ignore_index,
+                  float* lse, float* loss_rows, int M, alm_stream_t stream);
+
 /* One decode step of the WHOLE 4-stream hyper-connection stack (all layers: hyper-connection pre, q / kv projections,
  * value residual, cache append, attention over the static cache, out projection, feed-forward with GEGLU + LayerNorm,
  * final depth connection + LayerNorm) in ONE persistent cooperative kernel with device-wide barriers: what
