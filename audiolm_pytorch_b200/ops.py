@@ -295,7 +295,7 @@ def head_ce_fwd(x, w, bias, labels, ignore_index):
     lab = torch.empty(M, device=x.device, dtype=f32)
     lse = torch.empty(M, device=x.device, dtype=f32)
     rows = torch.empty(M, device=x.device, dtype=f32)
-    with _timed("gemm_bf16_tcgen05", 2.0 * M * V * K):
+    with _timed("gemm_head_ce_fused", 2.0 * M * V * K):
         _lib.call("alm_gemm_head_ce", x, x.stride(0), w, w.stride(0), bias, labels, int(ignore_index), 1, part, lab, None,
                   None, None, None, 0, M, V, K)
     _lib.call("alm_ce_finish", part, tiles, lab, labels, int(ignore_index), lse, rows, M)
@@ -310,8 +310,8 @@ def head_ce_bwd(x, w, bias, labels, ignore_index, lse, scale_num, scale_den, dlo
     V = w.shape[0]
     assert dlogits.dtype == bf16 and dlogits.shape[0] == M and dlogits.shape[1] >= V and dlogits.stride(1) == 1
     assert scale_num.dtype == f32 and scale_den.dtype == f32 and lse.dtype == f32
-    # the recomputation is executed work, not algorithmic work: it is timed in the GEMM class with 0 algorithmic FLOPs
-    with _timed("gemm_bf16_tcgen05", 0.0):
+    # the recomputation is executed work, not algorithmic work: timed in the fused-head class with 0 algorithmic FLOPs
+    with _timed("gemm_head_ce_fused", 0.0):
         _lib.call("alm_gemm_head_ce", x, x.stride(0), w, w.stride(0), bias, labels, int(ignore_index), 2, None, None, lse,
                   scale_num, scale_den, dlogits, dlogits.stride(0), M, V, K)
     return dlogits

@@ -420,7 +420,9 @@ def gemm_traffic_from_profile():
             continue
         total, ids = 0.0, set()
         for row in csv.reader(open(f, errors="replace")):
-            if len(row) >= 15 and row[0].isdigit() and "gemm_bf16_tcgen05" in row[4] and row[12].startswith("dram__bytes"):
+            # (the fused head + cross-entropy instantiation <BN, 0, 0, 1> is its own class, `gemm_head_ce_fused`)
+            if len(row) >= 15 and row[0].isdigit() and "gemm_bf16_tcgen05" in row[4] and ", 1>(" not in row[4] \
+                    and row[12].startswith("dram__bytes"):
                 total += float(row[14])
                 ids.add(row[0])
         if ids:
