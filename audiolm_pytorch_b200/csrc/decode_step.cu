@@ -136,13 +136,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16(v)); }
-__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float a) {
-  a = fmaf(bf16_lo(w.x), bf16_lo(x.x), a); a = fmaf(bf16_hi(w.x), bf16_hi(x.x), a);
-  a = fmaf(bf16_lo(w.y), bf16_lo(x.y), a); a = fmaf(bf16_hi(w.y), bf16_hi(x.y), a);
-  a = fmaf(bf16_lo(w.z), bf16_lo(x.z), a); a = fmaf(bf16_hi(w.z), bf16_hi(x.z), a);
-  a = fmaf(bf16_lo(w.w), bf16_lo(x.w), a); a = fmaf(bf16_hi(w.w), bf16_hi(x.w), a);
-  return a;
-}
 template <typename T>
 __device__ __forceinline__ T* tptr(const unsigned long long* lp, int i) {
   return reinterpret_cast<T*>(lp[i]);

@@ -177,3 +177,51 @@ def test_flat_grad_bucket_survives_zero_grad_set_to_none():
     assert torch.equal(b.flat[:12].view(3, 4), torch.full((3, 4), 2.0))
     b.zero_()
     assert float(m.weight.grad.abs().sum()) == 0.0
+
+
+def test_regroup_rows_layout_of_the_decode_step_operands():
+    """ops.regroup_rows: row (c * pc + l) of the copy is row (c + l * grid) of the operand, zero rows past N - the layout
+    alm_decode_stack_step documents in include/alm_b200.h (CTA c's rows of a projection become one contiguous block)."""
+    from audiolm_pytorch_b200 import ops
+
+    for N, K, grid in [(640, 16, 148), (5472, 8, 148), (7, 8, 4), (148, 8, 148), (149, 8, 148)]:
+        w = torch.arange(N * K, dtype=torch.float32).view(N, K)
+        wp = ops.regroup_rows(w, grid)
+        pc = -(-N // grid)
+        assert wp.shape == (grid * pc, K) and wp.is_contiguous()
+        for c in (0, 1, grid // 2, grid - 1):
+            for l in range(pc):
+                n = c + l * grid
+                want = w[n] if n < N else torch.zeros(K)
+                assert torch.equal(wp[c * pc + l], want), (N, grid, c, l)
+
+
+def test_deferred_heads_flag_is_scoped_to_the_loss_forward():
+    """the wrappers switch the transformers to LazyLogits only while they compute a loss; the flag is reset on exit and
+    on exceptions, and heads.FUSED_HEAD_CE = False disables it (public forward signatures stay the reference's)."""
+    from audiolm_pytorch_b200 import audiolm, heads
+
+    class T:
+        _defer_heads = False
+
+    t = T()
+    with audiolm._deferred_heads(t, True):
+        assert t._defer_heads is True
+    assert t._defer_heads is False
+    with audiolm._deferred_heads(t, False):
+        assert t._defer_heads is False
+    try:
+        with audiolm._deferred_heads(t, True):
+            raise RuntimeError("x")
+    except RuntimeError:
+        pass
+    assert t._defer_heads is False
+    heads.FUSED_HEAD_CE = False
+    try:
+        with audiolm._deferred_heads(t, True):
+            assert t._defer_heads is False
+    finally:
+        heads.FUSED_HEAD_CE = True
+    import inspect
+    for cls in (audiolm.SemanticTransformer, audiolm.CoarseTransformer, audiolm.FineTransformer):
+        assert not any(name.startswith("_") for name in inspect.signature(cls.forward).parameters if name != "self")
